@@ -1,0 +1,260 @@
+// extern "C" surface of libagym_b200 (see include/agym_b200.h): plan management, argument
+// validation and dispatch to the kernels.  No torch, no C++ types cross this boundary.
+#include <cmath>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "../../include/agym_b200.h"
+#include "agym_kernels.cuh"
+#include "agym_tables.h"
+
+using namespace agym;
+
+struct agym_plan {
+    agym_config cfg;
+    DevPlan dev;
+    void *pool = nullptr;  // device: every coefficient table, one allocation
+    size_t pool_bytes = 0;
+    int device = -1;
+};
+
+namespace {
+
+// Builder of the device pool: 32-bit words, every table 16-byte aligned.
+struct Pool {
+    std::vector<uint32_t> words;
+    size_t add_i(const std::vector<int32_t> &v) {
+        while (words.size() % 4) words.push_back(0);
+        const size_t off = words.size();
+        for (int32_t x : v) words.push_back(static_cast<uint32_t>(x));
+        return off;
+    }
+    size_t add_f(const std::vector<float> &v) {
+        while (words.size() % 4) words.push_back(0);
+        const size_t off = words.size();
+        for (float x : v) {
+            uint32_t u;
+            std::memcpy(&u, &x, 4);
+            words.push_back(u);
+        }
+        return off;
+    }
+};
+
+struct AxisOff {
+    size_t xmin, w;
+    int n_in, n_out, taps;
+};
+
+AxisOff add_axis(Pool &pool, int n_in, int n_out) {
+    const AaAxis ax = build_aa_axis(n_in, n_out);
+    return AxisOff{pool.add_i(ax.xmin), pool.add_f(ax.w), n_in, n_out, ax.taps};
+}
+
+AxisRef to_ref(const AxisOff &a, const uint32_t *base) {
+    AxisRef r;
+    r.xmin = reinterpret_cast<const int32_t *>(base + a.xmin);
+    r.w = reinterpret_cast<const float *>(base + a.w);
+    r.n_in = a.n_in; r.n_out = a.n_out; r.taps = a.taps;
+    return r;
+}
+
+int validate(const agym_config &c) {
+    if (c.n_envs <= 0 || c.frame_stack <= 0 || c.obs_h <= 0 || c.obs_w <= 0) return AGYM_ERR_INVALID_ARG;
+    if (c.raw_h <= 0 || c.raw_w <= 0 || (c.raw_c != 1 && c.raw_c != 3)) return AGYM_ERR_INVALID_ARG;
+    if (c.fov_h < 0 || c.fov_w < 0 || (c.fov_h == 0) != (c.fov_w == 0)) return AGYM_ERR_INVALID_ARG;
+    if (c.periph_h < 0 || c.periph_w < 0 || (c.periph_h == 0) != (c.periph_w == 0)) return AGYM_ERR_INVALID_ARG;
+    if (c.fov_h > 0) {
+        // assert (fov_size < obs_size).all()  (fov_env.py:112)
+        if (c.fov_h >= c.obs_h || c.fov_w >= c.obs_w) return AGYM_ERR_INVALID_ARG;
+        // the reference does not clamp fov_init_loc (fov_env.py:149-150) and returns a short
+        // crop when it is out of range; fixed-shape batched outputs cannot represent that
+        const double r = std::nearbyint(c.fov_init_loc[0]), q = std::nearbyint(c.fov_init_loc[1]);
+        if (!(r >= 0 && r <= c.obs_h - c.fov_h && q >= 0 && q <= c.obs_w - c.fov_w)) return AGYM_ERR_UNSUPPORTED;
+        if (c.relative && !(c.act_lo <= c.act_hi)) return AGYM_ERR_INVALID_ARG;
+    }
+    if (c.periph_h > 0 && c.fov_h == 0) return AGYM_ERR_INVALID_ARG;
+    // word/vector granularity the kernels are written for (84x84 obs, 210x160 raw satisfy all)
+    if (c.obs_w % 4 != 0 || (c.obs_h * c.obs_w) % 16 != 0) return AGYM_ERR_UNSUPPORTED;
+    if (c.obs_h > 255 || c.obs_w > 255 || c.raw_h > 4096 || c.raw_w > 4096) return AGYM_ERR_UNSUPPORTED;
+    return AGYM_OK;
+}
+
+inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
+inline int ret(cudaError_t e) { return e == cudaSuccess ? AGYM_OK : static_cast<int>(e); }
+
+}  // namespace
+
+extern "C" {
+
+int agym_abi_version(void) { return AGYM_ABI_VERSION; }
+
+const char *agym_status_string(int status) {
+    switch (status) {
+        case AGYM_OK: return "ok";
+        case AGYM_ERR_INVALID_ARG: return "invalid argument";
+        case AGYM_ERR_UNSUPPORTED: return "geometry not supported by the sm_100a kernels";
+        case AGYM_ERR_NO_DEVICE: return "no usable CUDA device";
+        case AGYM_ERR_ALLOC: return "allocation failed";
+        default: return status > 0 ? cudaGetErrorString(static_cast<cudaError_t>(status)) : "unknown status";
+    }
+}
+
+int agym_plan_create(const agym_config *cfg, agym_plan **out_plan) {
+    if (!cfg || !out_plan) return AGYM_ERR_INVALID_ARG;
+    *out_plan = nullptr;
+    const int v = validate(*cfg);
+    if (v != AGYM_OK) return v;
+    int dev = -1;
+    if (cudaGetDevice(&dev) != cudaSuccess) return AGYM_ERR_NO_DEVICE;
+
+    agym_plan *pl = new (std::nothrow) agym_plan();
+    if (!pl) return AGYM_ERR_ALLOC;
+    pl->cfg = *cfg;
+    pl->device = dev;
+    const agym_config &c = pl->cfg;
+
+    Pool pool;
+    // cv2.resize raw -> obs (atari_env.py:74).  Unused by the DMC path (raw == obs).
+    const Cv2Axis cx = build_cv2_axis(c.raw_w, c.obs_w, true), cy = build_cv2_axis(c.raw_h, c.obs_h, false);
+    const size_t o_xs0 = pool.add_i(cx.s0), o_xs1 = pool.add_i(cx.s1), o_xcf = pool.add_i(cx.coef);
+    const size_t o_ys0 = pool.add_i(cy.s0), o_ys1 = pool.add_i(cy.s1), o_ycf = pool.add_i(cy.coef);
+    AxisOff sq_w{}, sq_h{}, ex_w{}, ex_h{}, full_w{}, full_h{};
+    if (c.periph_h > 0) {
+        sq_w = add_axis(pool, c.obs_w, c.periph_w); sq_h = add_axis(pool, c.obs_h, c.periph_h);
+        ex_w = add_axis(pool, c.periph_w, c.obs_w); ex_h = add_axis(pool, c.periph_h, c.obs_h);
+    }
+    const int s_max = c.obs_h > c.obs_w ? c.obs_h : c.obs_w;
+    size_t o_flex = 0;
+    if (c.fov_h > 0) {
+        full_w = add_axis(pool, c.fov_w, c.obs_w); full_h = add_axis(pool, c.fov_h, c.obs_h);
+        // flexible fovea: for every window size r, r->f, f->r and r->S on both axes
+        std::vector<int32_t> index(static_cast<size_t>(2) * 3 * (s_max + 1) * 4, 0);
+        for (int axis = 0; axis < 2; ++axis) {
+            const int f = axis == 0 ? c.fov_h : c.fov_w, S = axis == 0 ? c.obs_h : c.obs_w;
+            for (int fam = 0; fam < 3; ++fam)
+                for (int r = 1; r <= S; ++r) {
+                    const int n_in = fam == 1 ? f : r, n_out = fam == 0 ? f : (fam == 1 ? r : S);
+                    const AxisOff a = add_axis(pool, n_in, n_out);
+                    int32_t *e = index.data() + (static_cast<size_t>(axis * 3 + fam) * (s_max + 1) + r) * 4;
+                    e[0] = static_cast<int32_t>(a.xmin); e[1] = static_cast<int32_t>(a.w); e[2] = a.taps; e[3] = a.n_out;
+                }
+        }
+        o_flex = pool.add_i(index);
+    }
+
+    pl->pool_bytes = pool.words.size() * 4;
+    if (cudaMalloc(&pl->pool, pl->pool_bytes) != cudaSuccess) { delete pl; return AGYM_ERR_ALLOC; }
+    const cudaError_t e = cudaMemcpy(pl->pool, pool.words.data(), pl->pool_bytes, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { cudaFree(pl->pool); delete pl; return static_cast<int>(e); }
+
+    const uint32_t *base = static_cast<const uint32_t *>(pl->pool);
+    DevPlan &d = pl->dev;
+    std::memset(&d, 0, sizeof(d));
+    d.N = c.n_envs; d.K = c.frame_stack; d.S_h = c.obs_h; d.S_w = c.obs_w; d.plane = c.obs_h * c.obs_w;
+    d.raw_h = c.raw_h; d.raw_w = c.raw_w; d.raw_c = c.raw_c;
+    d.lw0 = c.luma_w[0]; d.lw1 = c.luma_w[1]; d.lw2 = c.luma_w[2];
+    d.f_h = c.fov_h; d.f_w = c.fov_w; d.p_h = c.periph_h; d.p_w = c.periph_w;
+    d.relative = c.relative;
+    d.init_r = static_cast<int32_t>(std::nearbyint(c.fov_init_loc[0]));
+    d.init_c = static_cast<int32_t>(std::nearbyint(c.fov_init_loc[1]));
+    d.lo = c.act_lo; d.hi = c.act_hi;
+    auto ip = [&](size_t off) { return reinterpret_cast<const int32_t *>(base + off); };
+    d.cx_s0 = ip(o_xs0); d.cx_s1 = ip(o_xs1); d.cx_coef = ip(o_xcf);
+    d.cy_s0 = ip(o_ys0); d.cy_s1 = ip(o_ys1); d.cy_coef = ip(o_ycf);
+    if (c.periph_h > 0) {
+        d.sq_w = to_ref(sq_w, base); d.sq_h = to_ref(sq_h, base);
+        d.ex_w = to_ref(ex_w, base); d.ex_h = to_ref(ex_h, base);
+    }
+    if (c.fov_h > 0) {
+        d.full_w = to_ref(full_w, base); d.full_h = to_ref(full_h, base);
+        d.flex = reinterpret_cast<const FlexEntry *>(base + o_flex);
+    }
+    d.pool_i = reinterpret_cast<const int32_t *>(base);
+    d.S_max = s_max;
+    *out_plan = pl;
+    return AGYM_OK;
+}
+
+int agym_plan_destroy(agym_plan *plan) {
+    if (!plan) return AGYM_OK;
+    if (plan->pool) cudaFree(plan->pool);
+    delete plan;
+    return AGYM_OK;
+}
+
+size_t agym_plan_ring_bytes(const agym_plan *plan) {
+    return plan ? static_cast<size_t>(plan->cfg.n_envs) * plan->cfg.frame_stack * plan->cfg.obs_h * plan->cfg.obs_w : 0;
+}
+
+size_t agym_plan_pcache_bytes(const agym_plan *plan) {
+    return plan ? sizeof(float) * static_cast<size_t>(plan->cfg.n_envs) * plan->cfg.frame_stack * plan->cfg.periph_h *
+                      plan->cfg.periph_w
+                : 0;
+}
+
+int agym_ingest_atari(const agym_plan *plan, const uint8_t *d_frames_a, const uint8_t *d_frames_b,
+                      const uint8_t *d_flags, uint8_t *d_ring, int32_t *d_head, float *d_pcache, void *stream) {
+    if (!plan || !d_frames_a || !d_frames_b || !d_flags || !d_ring || !d_head) return AGYM_ERR_INVALID_ARG;
+    if (d_pcache && plan->cfg.periph_h == 0) return AGYM_ERR_INVALID_ARG;
+    if (plan->cfg.raw_w % 16 != 0) return AGYM_ERR_UNSUPPORTED;  // rows are staged as 16-byte vectors
+    return ret(launch_ingest_atari(plan->dev, d_frames_a, d_frames_b, d_flags, d_ring, d_head, d_pcache, as_stream(stream)));
+}
+
+int agym_ingest_dmc(const agym_plan *plan, const uint8_t *d_frames, const uint8_t *d_flags, uint8_t *d_ring,
+                    int32_t *d_head, float *d_pcache, void *stream) {
+    if (!plan || !d_frames || !d_flags || !d_ring || !d_head) return AGYM_ERR_INVALID_ARG;
+    const agym_config &c = plan->cfg;
+    if (c.raw_c != 3 || c.raw_h != c.obs_h || c.raw_w != c.obs_w) return AGYM_ERR_INVALID_ARG;  // rendered at obs_size
+    if (d_pcache && c.periph_h == 0) return AGYM_ERR_INVALID_ARG;
+    return ret(launch_ingest_dmc(plan->dev, d_frames, d_flags, d_ring, d_head, d_pcache, as_stream(stream)));
+}
+
+int agym_stack(const agym_plan *plan, const uint8_t *d_ring, const int32_t *d_head, uint8_t *d_out, void *stream) {
+    if (!plan || !d_ring || !d_head || !d_out) return AGYM_ERR_INVALID_ARG;
+    return ret(launch_stack(plan->dev, d_ring, d_head, d_out, as_stream(stream)));
+}
+
+static int check_fov_args(const agym_plan *plan, const void *ring, const void *head, const double *action,
+                          const uint8_t *ctrl, const void *loc, const void *out) {
+    if (!plan || !ring || !head || !loc || !out) return AGYM_ERR_INVALID_ARG;
+    if (plan->cfg.fov_h == 0) return AGYM_ERR_INVALID_ARG;
+    if (!action && !ctrl) return AGYM_ERR_INVALID_ARG;  // without actions every env must be RESET / KEEP
+    return AGYM_OK;
+}
+
+int agym_observe_fixed(const agym_plan *plan, const uint8_t *d_ring, const int32_t *d_head, const double *d_action,
+                       const uint8_t *d_fov_ctrl, int32_t *d_loc, int variant, uint8_t *d_out, void *stream) {
+    const int v = check_fov_args(plan, d_ring, d_head, d_action, d_fov_ctrl, d_loc, d_out);
+    if (v != AGYM_OK) return v;
+    if (variant < AGYM_OUT_CROP || variant > AGYM_OUT_RESIZE_FULL) return AGYM_ERR_INVALID_ARG;
+    return ret(launch_observe_fixed(plan->dev, d_ring, d_head, d_action, d_fov_ctrl, d_loc, variant, d_out, as_stream(stream)));
+}
+
+int agym_observe_peripheral(const agym_plan *plan, const uint8_t *d_ring, const int32_t *d_head, const float *d_pcache,
+                            const double *d_action, const uint8_t *d_fov_ctrl, int32_t *d_loc, uint8_t *d_out,
+                            void *stream) {
+    const int v = check_fov_args(plan, d_ring, d_head, d_action, d_fov_ctrl, d_loc, d_out);
+    if (v != AGYM_OK) return v;
+    if (plan->cfg.periph_h == 0) return AGYM_ERR_INVALID_ARG;
+    return ret(launch_observe_peripheral(plan->dev, d_ring, d_head, d_pcache, d_action, d_fov_ctrl, d_loc, d_out, as_stream(stream)));
+}
+
+int agym_observe_flexible(const agym_plan *plan, const uint8_t *d_ring, const int32_t *d_head, const double *d_action,
+                          const int32_t *d_atype, const uint8_t *d_fov_ctrl, int32_t *d_loc, int32_t *d_res, int variant,
+                          int pad_h, int pad_w, uint8_t *d_out, void *stream) {
+    const int v = check_fov_args(plan, d_ring, d_head, d_action, d_fov_ctrl, d_loc, d_out);
+    if (v != AGYM_OK) return v;
+    if (!d_res || variant < AGYM_OUT_CROP || variant > AGYM_OUT_RESIZE_FULL) return AGYM_ERR_INVALID_ARG;
+    if (variant == AGYM_OUT_CROP && (pad_h <= 0 || pad_w <= 0 || pad_w % 4 != 0)) return AGYM_ERR_INVALID_ARG;
+    return ret(launch_observe_flexible(plan->dev, d_ring, d_head, d_action, d_atype, d_fov_ctrl, d_loc, d_res, variant,
+                                       pad_h, pad_w, d_out, as_stream(stream)));
+}
+
+int agym_synth_frames(uint8_t *d_dst, size_t n_bytes, uint64_t seed, void *stream) {
+    if (!d_dst || n_bytes % 16 != 0) return AGYM_ERR_INVALID_ARG;
+    return ret(launch_synth(d_dst, n_bytes, seed, as_stream(stream)));
+}
+
+}  // extern "C"

@@ -1,0 +1,709 @@
+// sm_100a kernels of the active-perception observation path.
+//
+// Every kernel here is a byte/integer streaming kernel bounded by HBM bandwidth or by
+// instruction issue — there is no dense contraction on this path, so no tensor cores.
+// Mapping: one CTA per environment; the env's source tile is staged in shared memory with
+// coalesced 16-byte loads, all variable-offset (fovea) accesses are served from shared memory
+// or from L2-resident rows, and outputs leave as whole 4/16-byte words.
+//
+// Reference semantics (file:line relative to /root/reference/active_gym/) are cited at each
+// kernel; the arithmetic must stay bit-identical to oracle/agym_oracle.c for the integer
+// stages (cv2 resize, luma, max, stack, crop, mask, paste) and within 0.5 u8 LSB + fp32
+// round-off of it for the antialiased resamples.
+#include "agym_kernels.cuh"
+
+#include "../../include/agym_b200.h"
+
+namespace agym {
+
+namespace {
+
+constexpr int kThreads = 256;
+
+__device__ __forceinline__ uint4 ld_stream128(const void *p) {
+    // read-once data (raw simulator frames): bypass L1 allocation
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+
+struct FastDiv {
+    uint32_t magic;
+    int32_t d;
+    __device__ __forceinline__ explicit FastDiv(int32_t dd) : magic(0xFFFFFFFFu / (uint32_t)dd + 1u), d(dd) {}
+    // exact for n * d < 2^32 (all indices here are < 2^24, divisors < 2^8)
+    __device__ __forceinline__ int32_t div(int32_t n) const { return d == 1 ? n : (int32_t)__umulhi((uint32_t)n, magic); }
+};
+
+__device__ __forceinline__ int clip_rint(double v, double lo, double hi) {
+    // np.rint(np.clip(v, lo, hi)): clip first, then round half to even (fov_env.py:166-170)
+    return __double2int_rn(fmin(fmax(v, lo), hi));
+}
+
+__device__ __forceinline__ uint32_t quant_u8(float v) {
+    int q = __float2int_rn(v);
+    return (uint32_t)min(max(q, 0), 255);
+}
+
+// fov_loc update of the fixed fovea, run by one thread per env (fov_env.py:187-199).
+__device__ void update_loc_fixed(const DevPlan &p, int n, const double *action, const uint8_t *ctrl, int32_t *loc,
+                                 int &r, int &c) {
+    const int mode = ctrl ? ctrl[n] : AGYM_FOV_APPLY;
+    r = loc[2 * n];
+    c = loc[2 * n + 1];
+    if (mode == AGYM_FOV_RESET) {
+        r = p.init_r;
+        c = p.init_c;
+    } else if (mode == AGYM_FOV_APPLY) {
+        double a0 = action[2 * n], a1 = action[2 * n + 1];
+        if (p.relative) {
+            a0 = (double)(r + clip_rint(a0, p.lo, p.hi));
+            a1 = (double)(c + clip_rint(a1, p.lo, p.hi));
+        }
+        r = clip_rint(a0, 0.0, (double)(p.S_h - p.f_h));
+        c = clip_rint(a1, 0.0, (double)(p.S_w - p.f_w));
+    }
+    loc[2 * n] = r;
+    loc[2 * n + 1] = c;
+}
+
+// ------------------------------------------------------------------ separable resamples
+// dst[r][c] = sum_j w[c][j] * src[r][xmin[c] + j]      (pass along the contiguous axis)
+template <typename SrcT>
+__device__ __forceinline__ void resample_w(const SrcT *src, int sstride, float *dst, int dstride, int rows,
+                                           const AxisRef &ax, int tid, int nt) {
+    const int total = rows * ax.n_out;
+    const FastDiv fd(ax.n_out);
+    for (int i = tid; i < total; i += nt) {
+        const int r = fd.div(i), c = i - r * ax.n_out;
+        const SrcT *s = src + r * sstride + __ldg(ax.xmin + c);
+        const float *w = ax.w + c * ax.taps;
+        float acc = 0.f;
+        for (int j = 0; j < ax.taps; ++j) acc = fmaf(__ldg(w + j), (float)s[j], acc);
+        dst[r * dstride + c] = acc;
+    }
+}
+
+// dst[r][c] = sum_j w[r][j] * src[xmin[r] + j][c]      (pass along the strided axis)
+template <typename SrcT>
+__device__ __forceinline__ void resample_h(const SrcT *src, int sstride, float *dst, int dstride, int cols,
+                                           const AxisRef &ax, int tid, int nt) {
+    const int total = ax.n_out * cols;
+    const FastDiv fd(cols);
+    for (int i = tid; i < total; i += nt) {
+        const int r = fd.div(i), c = i - r * cols;
+        const SrcT *s = src + __ldg(ax.xmin + r) * sstride + c;
+        const float *w = ax.w + r * ax.taps;
+        float acc = 0.f;
+        for (int j = 0; j < ax.taps; ++j) acc = fmaf(__ldg(w + j), (float)s[j * sstride], acc);
+        dst[r * dstride + c] = acc;
+    }
+}
+
+// One output word (4 pixels of row y starting at column x0) of a strided-axis pass.
+__device__ __forceinline__ uint32_t resample_h_word(const float *src, int sstride, const AxisRef &ax, int y, int x0) {
+    const float *s = src + __ldg(ax.xmin + y) * sstride + x0;
+    const float *w = ax.w + y * ax.taps;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    for (int j = 0; j < ax.taps; ++j) {
+        const float wj = __ldg(w + j);
+        const float *sj = s + j * sstride;
+        a0 = fmaf(wj, sj[0], a0);
+        a1 = fmaf(wj, sj[1], a1);
+        a2 = fmaf(wj, sj[2], a2);
+        a3 = fmaf(wj, sj[3], a3);
+    }
+    return quant_u8(a0) | (quant_u8(a1) << 8) | (quant_u8(a2) << 16) | (quant_u8(a3) << 24);
+}
+
+// byte mask of the columns [c0, c1) inside the 4-byte word that starts at column x0
+__device__ __forceinline__ uint32_t word_mask(int x0, int c0, int c1) {
+    const int lo = max(c0 - x0, 0), hi = min(c1 - x0, 4);
+    if (lo >= hi) return 0u;
+    const uint32_t upto_hi = hi >= 4 ? 0xFFFFFFFFu : ((1u << (8 * hi)) - 1u);
+    return upto_hi & ~((1u << (8 * lo)) - 1u);
+}
+
+__device__ __forceinline__ size_t align16(size_t v) { return (v + 15) & ~size_t(15); }
+
+// Squeeze of one obs frame held in shared memory (u8) into the peripheral cache slot:
+// Resize(peripheral_res) = W pass then H pass (fov_env.py:367).  Needs t1[S_h * p_w] floats.
+__device__ void squeeze_to_cache(const DevPlan &p, const uint8_t *s_frame, float *s_t1, float *dst_global, int tid, int nt) {
+    resample_w<uint8_t>(s_frame, p.S_w, s_t1, p.p_w, p.S_h, p.sq_w, tid, nt);
+    __syncthreads();
+    resample_h<float>(s_t1, p.p_w, dst_global, p.p_w, p.p_w, p.sq_h, tid, nt);
+}
+
+// ------------------------------------------------------------------------ ingest: Atari
+// AtariEnv._get_state + the frame logic of _step/_reset (atari_env.py:73-75, 80-82, 91,
+// 111-114, 121-133): gray -> cv2.resize(INTER_LINEAR) for frame A and frame B separately,
+// max of the two resized frames, push.  Shared memory holds, per frame, only the two source
+// rows every output row samples (raw rows the resize never reads are not fetched).
+template <int CH>
+__global__ void __launch_bounds__(kThreads) k_ingest_atari(const __grid_constant__ DevPlan p,
+                                                           const uint8_t *__restrict__ fa,
+                                                           const uint8_t *__restrict__ fb,
+                                                           const uint8_t *__restrict__ flags, uint8_t *__restrict__ ring,
+                                                           int32_t *__restrict__ head, float *__restrict__ pcache) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int n = blockIdx.x, tid = threadIdx.x;
+    const int fl = flags[n];
+    if (fl & AGYM_FLAG_IDLE) return;
+    const int slot = (head[n] + 1) % p.K;
+
+    int32_t *t_xs0 = reinterpret_cast<int32_t *>(smem);
+    int32_t *t_xs1 = t_xs0 + p.S_w, *t_xcf = t_xs1 + p.S_w;
+    int32_t *t_ys0 = t_xcf + p.S_w, *t_ys1 = t_ys0 + p.S_h, *t_ycf = t_ys1 + p.S_h;
+    uint8_t *s_gray = smem + align16(sizeof(int32_t) * 3 * (p.S_w + p.S_h));
+    const int rows2 = 2 * p.S_h;                       // staged rows per frame
+    const size_t gray_bytes = (size_t)rows2 * p.raw_w; // per frame
+    uint8_t *s_frame = s_gray + align16(2 * gray_bytes);
+    float *s_t1 = reinterpret_cast<float *>(s_frame + align16(p.plane));
+
+    for (int i = tid; i < p.S_w; i += kThreads) {
+        t_xs0[i] = p.cx_s0[i]; t_xs1[i] = p.cx_s1[i]; t_xcf[i] = p.cx_coef[i];
+    }
+    for (int i = tid; i < p.S_h; i += kThreads) {
+        t_ys0[i] = p.cy_s0[i]; t_ys1[i] = p.cy_s1[i]; t_ycf[i] = p.cy_coef[i];
+    }
+    __syncthreads();  // also orders every thread's read of head[n] before the update below
+    if (tid == 0) head[n] = slot;
+
+    // ---- stage: gray rows of the valid frames -> shared memory
+    const int vpr = p.raw_w / 16;  // 16-pixel groups per row
+    const FastDiv fd_vpr(vpr);
+    const size_t frame_bytes = (size_t)p.raw_h * p.raw_w * CH;
+#pragma unroll 1
+    for (int fr = 0; fr < 2; ++fr) {
+        if (!(fl & (1 << fr))) continue;
+        const uint8_t *src = (fr ? fb : fa) + frame_bytes * n;
+        uint8_t *dst = s_gray + gray_bytes * fr;
+#pragma unroll 2
+        for (int t = tid; t < rows2 * vpr; t += kThreads) {
+            const int sr = fd_vpr.div(t), g = t - sr * vpr;
+            const int srow = (sr & 1) ? t_ys1[sr >> 1] : t_ys0[sr >> 1];
+            uint4 o;
+            if (CH == 1) {
+                o = ld_stream128(src + (size_t)srow * p.raw_w + 16 * g);
+            } else {
+                const uint8_t *q = src + ((size_t)srow * p.raw_w + 16 * g) * 3;
+                uint32_t w[12];
+                *reinterpret_cast<uint4 *>(w) = ld_stream128(q);
+                *reinterpret_cast<uint4 *>(w + 4) = ld_stream128(q + 16);
+                *reinterpret_cast<uint4 *>(w + 8) = ld_stream128(q + 32);
+                uint32_t out[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const int j = 3 * i;
+                    const uint32_t c0 = (w[j >> 2] >> (8 * (j & 3))) & 0xffu;
+                    const uint32_t c1 = (w[(j + 1) >> 2] >> (8 * ((j + 1) & 3))) & 0xffu;
+                    const uint32_t c2 = (w[(j + 2) >> 2] >> (8 * ((j + 2) & 3))) & 0xffu;
+                    const uint32_t yv = (p.lw0 * c0 + p.lw1 * c1 + p.lw2 * c2 + 16384u) >> 15;
+                    out[i >> 2] |= yv << (8 * (i & 3));
+                }
+                o = make_uint4(out[0], out[1], out[2], out[3]);
+            }
+            *reinterpret_cast<uint4 *>(dst + (size_t)sr * p.raw_w + 16 * g) = o;
+        }
+    }
+    // hard reset: the other K-1 slots (and their cache entries) become zero frames
+    if (fl & AGYM_FLAG_HARD_RESET) {
+        const int words = p.plane / 4;
+        for (int k = 0; k < p.K; ++k) {
+            if (k == slot) continue;
+            uint32_t *z = reinterpret_cast<uint32_t *>(ring + ((size_t)n * p.K + k) * p.plane);
+            for (int i = tid; i < words; i += kThreads) z[i] = 0u;
+            if (pcache) {
+                float *zc = pcache + ((size_t)n * p.K + k) * p.p_h * p.p_w;
+                for (int i = tid; i < p.p_h * p.p_w; i += kThreads) zc[i] = 0.f;
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- resize both frames (11-bit fixed point, horizontal then vertical), max, store
+    const int wpr = p.S_w / 4;  // output words per row
+    const FastDiv fd_wpr(wpr);
+    uint32_t *out_words = reinterpret_cast<uint32_t *>(ring + ((size_t)n * p.K + slot) * p.plane);
+    uint32_t *frame_words = reinterpret_cast<uint32_t *>(s_frame);
+    for (int t = tid; t < p.plane / 4; t += kThreads) {
+        const int y = fd_wpr.div(t), q = t - y * wpr;
+        const int ycf = t_ycf[y];
+        const int b0 = ycf & 0xffff, b1 = ycf >> 16;
+        uint32_t word = 0u;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int x = 4 * q + i;
+            const int s0 = t_xs0[x], s1 = t_xs1[x], xcf = t_xcf[x];
+            const int c0 = xcf & 0xffff, c1 = xcf >> 16;
+            int m = 0;
+#pragma unroll
+            for (int fr = 0; fr < 2; ++fr) {
+                if (!(fl & (1 << fr))) continue;
+                const uint8_t *r0 = s_gray + gray_bytes * fr + (size_t)(2 * y) * p.raw_w;
+                const uint8_t *r1 = r0 + p.raw_w;
+                const int h0 = r0[s0] * c0 + r0[s1] * c1;
+                const int h1 = r1[s0] * c0 + r1[s1] * c1;
+                const int v = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
+                m = max(m, v);
+            }
+            word |= (uint32_t)min(m, 255) << (8 * i);
+        }
+        out_words[t] = word;
+        if (pcache) frame_words[t] = word;
+    }
+    if (pcache) {  // uniform branch
+        __syncthreads();
+        squeeze_to_cache(p, s_frame, s_t1, pcache + ((size_t)n * p.K + slot) * p.p_h * p.p_w, tid, kThreads);
+    }
+}
+
+// -------------------------------------------------------------------------- ingest: DMC
+// DMCEnv._get_obs pixel/grey branch + stack logic (dmc_env.py:175-183, 193-195, 206-207,
+// 228-230): 15-bit luma of the frame rendered at obs_size, pushed as is (no max-pool).
+__global__ void __launch_bounds__(kThreads) k_ingest_dmc(const __grid_constant__ DevPlan p,
+                                                         const uint8_t *__restrict__ f, const uint8_t *__restrict__ flags,
+                                                         uint8_t *__restrict__ ring, int32_t *__restrict__ head,
+                                                         float *__restrict__ pcache) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int n = blockIdx.x, tid = threadIdx.x;
+    const int fl = flags[n];
+    if (fl & AGYM_FLAG_IDLE) return;
+    const int slot = (head[n] + 1) % p.K;
+    uint8_t *s_frame = smem;
+    float *s_t1 = reinterpret_cast<float *>(smem + align16(p.plane));
+    __syncthreads();
+    if (tid == 0) head[n] = slot;
+
+    const uint8_t *src = f + (size_t)n * p.plane * 3;
+    uint4 *dst = reinterpret_cast<uint4 *>(ring + ((size_t)n * p.K + slot) * p.plane);
+#pragma unroll 2
+    for (int t = tid; t < p.plane / 16; t += kThreads) {
+        uint32_t w[12];
+        const uint8_t *q = src + (size_t)t * 48;
+        *reinterpret_cast<uint4 *>(w) = ld_stream128(q);
+        *reinterpret_cast<uint4 *>(w + 4) = ld_stream128(q + 16);
+        *reinterpret_cast<uint4 *>(w + 8) = ld_stream128(q + 32);
+        uint32_t out[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const int j = 3 * i;
+            const uint32_t c0 = (w[j >> 2] >> (8 * (j & 3))) & 0xffu;
+            const uint32_t c1 = (w[(j + 1) >> 2] >> (8 * ((j + 1) & 3))) & 0xffu;
+            const uint32_t c2 = (w[(j + 2) >> 2] >> (8 * ((j + 2) & 3))) & 0xffu;
+            const uint32_t yv = (p.lw0 * c0 + p.lw1 * c1 + p.lw2 * c2 + 16384u) >> 15;
+            out[i >> 2] |= yv << (8 * (i & 3));
+        }
+        const uint4 o = make_uint4(out[0], out[1], out[2], out[3]);
+        dst[t] = o;
+        if (pcache) reinterpret_cast<uint4 *>(s_frame)[t] = o;
+    }
+    if (fl & AGYM_FLAG_HARD_RESET) {
+        for (int k = 0; k < p.K; ++k) {
+            if (k == slot) continue;
+            uint4 *z = reinterpret_cast<uint4 *>(ring + ((size_t)n * p.K + k) * p.plane);
+            for (int i = tid; i < p.plane / 16; i += kThreads) z[i] = make_uint4(0u, 0u, 0u, 0u);
+            if (pcache) {
+                float *zc = pcache + ((size_t)n * p.K + k) * p.p_h * p.p_w;
+                for (int i = tid; i < p.p_h * p.p_w; i += kThreads) zc[i] = 0.f;
+            }
+        }
+    }
+    if (pcache) {
+        __syncthreads();
+        squeeze_to_cache(p, s_frame, s_t1, pcache + ((size_t)n * p.K + slot) * p.p_h * p.p_w, tid, kThreads);
+    }
+}
+
+// ------------------------------------------------------------------------------- stack
+// np.stack(state_buffer) (atari_env.py:143, dmc_env.py:230): oldest -> newest.
+__global__ void __launch_bounds__(kThreads) k_stack(const __grid_constant__ DevPlan p, const uint8_t *__restrict__ ring,
+                                                    const int32_t *__restrict__ head, uint8_t *__restrict__ out) {
+    const int n = blockIdx.x;
+    const int h = head[n];
+    const int vpp = p.plane / 16;
+    for (int k = 0; k < p.K; ++k) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(ring + ((size_t)n * p.K + (h + 1 + k) % p.K) * p.plane);
+        uint4 *dst = reinterpret_cast<uint4 *>(out + ((size_t)n * p.K + k) * p.plane);
+        for (int i = threadIdx.x; i < vpp; i += kThreads) dst[i] = __ldg(src + i);
+    }
+}
+
+// ------------------------------------------------------------------------ observe: fixed
+// FixedFovealEnv._fov_step + _get_fov_state (fov_env.py:166-203).
+template <int VARIANT>
+__global__ void __launch_bounds__(kThreads) k_observe_fixed(const __grid_constant__ DevPlan p,
+                                                            const uint8_t *__restrict__ ring,
+                                                            const int32_t *__restrict__ head,
+                                                            const double *__restrict__ action,
+                                                            const uint8_t *__restrict__ ctrl, int32_t *__restrict__ loc,
+                                                            uint8_t *__restrict__ out) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    __shared__ int s_loc[2];
+    const int n = blockIdx.x, tid = threadIdx.x;
+    if (tid == 0) {
+        int r, c;
+        update_loc_fixed(p, n, action, ctrl, loc, r, c);
+        s_loc[0] = r; s_loc[1] = c;
+    }
+    __syncthreads();
+    const int r0 = s_loc[0], c0 = s_loc[1];
+    const int h = head[n];
+    const uint8_t *env_ring = ring + (size_t)n * p.K * p.plane;
+
+    if (VARIANT == AGYM_OUT_CROP) {
+        // (K, f_h, f_w) packed; bytes gathered from the (L2-resident) ring rows
+        const int per_k = p.f_h * p.f_w, total = p.K * per_k;
+        const FastDiv fd_k(per_k), fd_w(p.f_w);
+        uint8_t *dst = out + (size_t)n * total;
+        if ((total & 3) == 0) {
+            for (int t = tid; t < total / 4; t += kThreads) {
+                uint32_t word = 0u;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int b = 4 * t + i;
+                    const int k = fd_k.div(b), rem = b - k * per_k;
+                    const int y = fd_w.div(rem), x = rem - y * p.f_w;
+                    const uint8_t *src = env_ring + (size_t)((h + 1 + k) % p.K) * p.plane;
+                    word |= (uint32_t)__ldg(src + (r0 + y) * p.S_w + c0 + x) << (8 * i);
+                }
+                reinterpret_cast<uint32_t *>(dst)[t] = word;
+            }
+        } else {
+            for (int b = tid; b < total; b += kThreads) {
+                const int k = fd_k.div(b), rem = b - k * per_k;
+                const int y = fd_w.div(rem), x = rem - y * p.f_w;
+                const uint8_t *src = env_ring + (size_t)((h + 1 + k) % p.K) * p.plane;
+                dst[b] = __ldg(src + (r0 + y) * p.S_w + c0 + x);
+            }
+        }
+    } else if (VARIANT == AGYM_OUT_MASK) {
+        // (K, S_h, S_w): the ring word where it lies inside the fovea, zero elsewhere
+        const int wpr = p.S_w / 4, wpp = p.plane / 4;
+        const FastDiv fd_wpr(wpr);
+        for (int k = 0; k < p.K; ++k) {
+            const uint32_t *src = reinterpret_cast<const uint32_t *>(env_ring + (size_t)((h + 1 + k) % p.K) * p.plane);
+            uint32_t *dst = reinterpret_cast<uint32_t *>(out + ((size_t)n * p.K + k) * p.plane);
+            for (int t = tid; t < wpp; t += kThreads) {
+                const int y = fd_wpr.div(t), x0 = 4 * (t - y * wpr);
+                uint32_t m = 0u;
+                if (y >= r0 && y < r0 + p.f_h) m = word_mask(x0, c0, c0 + p.f_w);
+                dst[t] = m ? (__ldg(src + t) & m) : 0u;
+            }
+        }
+    } else {
+        // resize_to_full: Resize(obs_size) of the crop, W pass then H pass (fov_env.py:120,182)
+        float *s_crop = reinterpret_cast<float *>(smem);
+        float *s_t = s_crop + p.f_h * p.f_w;
+        const int wpr = p.S_w / 4, wpp = p.plane / 4;
+        const FastDiv fd_fw(p.f_w), fd_wpr(wpr);
+        for (int k = 0; k < p.K; ++k) {
+            const uint8_t *src = env_ring + (size_t)((h + 1 + k) % p.K) * p.plane;
+            for (int i = tid; i < p.f_h * p.f_w; i += kThreads) {
+                const int y = fd_fw.div(i), x = i - y * p.f_w;
+                s_crop[i] = (float)__ldg(src + (r0 + y) * p.S_w + c0 + x);
+            }
+            __syncthreads();
+            resample_w<float>(s_crop, p.f_w, s_t, p.S_w, p.f_h, p.full_w, tid, kThreads);
+            __syncthreads();
+            uint32_t *dst = reinterpret_cast<uint32_t *>(out + ((size_t)n * p.K + k) * p.plane);
+            for (int t = tid; t < wpp; t += kThreads) {
+                const int y = fd_wpr.div(t), x0 = 4 * (t - y * wpr);
+                dst[t] = resample_h_word(s_t, p.S_w, p.full_h, y, x0);
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// ------------------------------------------------------------------- observe: peripheral
+// FixedFovealPeripheralEnv._get_fov_state (fov_env.py:375-388):
+//   out = Resize(obs)(Resize(peripheral_res)(full)); out[fovea] = full[fovea].
+// CACHED: the squeeze of every ring slot was stored at ingest time (it does not depend on
+// fov_loc), so only the expand + paste remain per step.
+template <bool CACHED>
+__global__ void __launch_bounds__(kThreads) k_observe_peripheral(const __grid_constant__ DevPlan p,
+                                                                 const uint8_t *__restrict__ ring,
+                                                                 const int32_t *__restrict__ head,
+                                                                 const float *__restrict__ pcache,
+                                                                 const double *__restrict__ action,
+                                                                 const uint8_t *__restrict__ ctrl,
+                                                                 int32_t *__restrict__ loc, uint8_t *__restrict__ out) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    __shared__ int s_loc[2];
+    const int n = blockIdx.x, tid = threadIdx.x;
+    if (tid == 0) {
+        int r, c;
+        update_loc_fixed(p, n, action, ctrl, loc, r, c);
+        s_loc[0] = r; s_loc[1] = c;
+    }
+    __syncthreads();
+    const int r0 = s_loc[0], c0 = s_loc[1];
+    const int h = head[n];
+
+    // shared: frame u8 [plane] | t1 f32 [S_h][p_w] | sq f32 [p_h][p_w] | t2 f32 [p_h][S_w]
+    uint8_t *s_frame = smem;
+    float *s_t1 = reinterpret_cast<float *>(smem + align16(p.plane));
+    float *s_sq = s_t1 + p.S_h * p.p_w;
+    float *s_t2 = s_sq + p.p_h * p.p_w;
+    const int wpr = p.S_w / 4, wpp = p.plane / 4;
+    const FastDiv fd_wpr(wpr);
+
+    for (int k = 0; k < p.K; ++k) {
+        const int slot = (h + 1 + k) % p.K;
+        const uint8_t *src = ring + ((size_t)n * p.K + slot) * p.plane;
+        if (!CACHED) {
+            for (int i = tid; i < p.plane / 16; i += kThreads)
+                reinterpret_cast<uint4 *>(s_frame)[i] = __ldg(reinterpret_cast<const uint4 *>(src) + i);
+            __syncthreads();
+            resample_w<uint8_t>(s_frame, p.S_w, s_t1, p.p_w, p.S_h, p.sq_w, tid, kThreads);
+            __syncthreads();
+            resample_h<float>(s_t1, p.p_w, s_sq, p.p_w, p.p_w, p.sq_h, tid, kThreads);
+            __syncthreads();
+        } else {
+            const float *c = pcache + ((size_t)n * p.K + slot) * p.p_h * p.p_w;
+            for (int i = tid; i < p.p_h * p.p_w; i += kThreads) s_sq[i] = __ldg(c + i);
+            __syncthreads();
+        }
+        resample_w<float>(s_sq, p.p_w, s_t2, p.S_w, p.p_h, p.ex_w, tid, kThreads);
+        __syncthreads();
+        uint32_t *dst = reinterpret_cast<uint32_t *>(out + ((size_t)n * p.K + k) * p.plane);
+        const uint32_t *sharp_g = reinterpret_cast<const uint32_t *>(src);
+        const uint32_t *sharp_s = reinterpret_cast<const uint32_t *>(s_frame);
+        for (int t = tid; t < wpp; t += kThreads) {
+            const int y = fd_wpr.div(t), x0 = 4 * (t - y * wpr);
+            uint32_t v = resample_h_word(s_t2, p.S_w, p.ex_h, y, x0);
+            if (y >= r0 && y < r0 + p.f_h) {
+                const uint32_t m = word_mask(x0, c0, c0 + p.f_w);
+                if (m) v = (v & ~m) | ((CACHED ? __ldg(sharp_g + t) : sharp_s[t]) & m);
+            }
+            dst[t] = v;
+        }
+        __syncthreads();
+    }
+}
+
+// --------------------------------------------------------------------- observe: flexible
+// FlexibleFovealEnv._fov_step + _get_fov_state (fov_env.py:270-330).
+__device__ __forceinline__ AxisRef flex_axis(const DevPlan &p, int axis, int family, int r, int n_in) {
+    const FlexEntry e = p.flex[(axis * 3 + family) * (p.S_max + 1) + r];
+    AxisRef a;
+    a.xmin = p.pool_i + e.xmin_off;
+    a.w = reinterpret_cast<const float *>(p.pool_i + e.w_off);
+    a.n_in = n_in; a.n_out = e.n_out; a.taps = e.taps;
+    return a;
+}
+
+template <int VARIANT>
+__global__ void __launch_bounds__(kThreads) k_observe_flexible(const __grid_constant__ DevPlan p,
+                                                               const uint8_t *__restrict__ ring,
+                                                               const int32_t *__restrict__ head,
+                                                               const double *__restrict__ action,
+                                                               const int32_t *__restrict__ atype,
+                                                               const uint8_t *__restrict__ ctrl,
+                                                               int32_t *__restrict__ loc, int32_t *__restrict__ res,
+                                                               int pad_h, int pad_w, uint8_t *__restrict__ out) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    __shared__ int s_win[4];
+    const int n = blockIdx.x, tid = threadIdx.x;
+    if (tid == 0) {
+        const int mode = ctrl ? ctrl[n] : AGYM_FOV_APPLY;
+        int r = loc[2 * n], c = loc[2 * n + 1], rh = res[2 * n], rw = res[2 * n + 1];
+        if (mode == AGYM_FOV_RESET) {
+            r = p.init_r; c = p.init_c; rh = p.f_h; rw = p.f_w;
+        } else if (mode == AGYM_FOV_APPLY) {
+            const double a0 = action[2 * n], a1 = action[2 * n + 1];
+            const int t = atype ? atype[n] : AGYM_ATYPE_FOV_LOC;
+            if (t == AGYM_ATYPE_FOV_RES) {
+                // fov_res = action (fov_env.py:323); the reference raises for res > obs, the
+                // device clamps to [1, S] instead (the Python layer validates beforehand)
+                rh = min(max((int)a0, 1), p.S_h);
+                rw = min(max((int)a1, 1), p.S_w);
+                r = clip_rint((double)r, 0.0, (double)(p.S_h - rh));
+                c = clip_rint((double)c, 0.0, (double)(p.S_w - rw));
+            } else {
+                double v0 = a0, v1 = a1;
+                if (p.relative) {
+                    v0 = (double)(r + clip_rint(a0, p.lo, p.hi));
+                    v1 = (double)(c + clip_rint(a1, p.lo, p.hi));
+                }
+                r = clip_rint(v0, 0.0, (double)(p.S_h - rh));
+                c = clip_rint(v1, 0.0, (double)(p.S_w - rw));
+            }
+        }
+        loc[2 * n] = r; loc[2 * n + 1] = c; res[2 * n] = rh; res[2 * n + 1] = rw;
+        s_win[0] = r; s_win[1] = c; s_win[2] = rh; s_win[3] = rw;
+    }
+    __syncthreads();
+    const int r0 = s_win[0], c0 = s_win[1], rh = s_win[2], rw = s_win[3];
+    const int h = head[n];
+    const bool blur = rh > p.f_h;  // row dimension only (fov_env.py:286)
+
+    float *bufA = reinterpret_cast<float *>(smem);
+    float *bufB = bufA + p.plane;
+    const FastDiv fd_rw(rw);
+    const int oh = VARIANT == AGYM_OUT_CROP ? pad_h : p.S_h, ow = VARIANT == AGYM_OUT_CROP ? pad_w : p.S_w;
+    const int oy = VARIANT == AGYM_OUT_MASK ? r0 : 0, ox = VARIANT == AGYM_OUT_MASK ? c0 : 0;
+    const int wpr = ow / 4, wpp = oh * ow / 4;
+    const FastDiv fd_wpr(wpr);
+
+    for (int k = 0; k < p.K; ++k) {
+        const uint8_t *src = ring + ((size_t)n * p.K + (h + 1 + k) % p.K) * p.plane;
+        for (int i = tid; i < rh * rw; i += kThreads) {
+            const int y = fd_rw.div(i), x = i - y * rw;
+            bufA[i] = (float)__ldg(src + (r0 + y) * p.S_w + c0 + x);
+        }
+        __syncthreads();
+        if (blur) {  // Resize(fov_size) then Resize(fov_res) (fov_env.py:276-280)
+            resample_w<float>(bufA, rw, bufB, p.f_w, rh, flex_axis(p, 1, 0, rw, rw), tid, kThreads);
+            __syncthreads();
+            resample_h<float>(bufB, p.f_w, bufA, p.f_w, p.f_w, flex_axis(p, 0, 0, rh, rh), tid, kThreads);
+            __syncthreads();
+            resample_w<float>(bufA, p.f_w, bufB, rw, p.f_h, flex_axis(p, 1, 1, rw, p.f_w), tid, kThreads);
+            __syncthreads();
+            resample_h<float>(bufB, rw, bufA, rw, rw, flex_axis(p, 0, 1, rh, p.f_h), tid, kThreads);
+            __syncthreads();
+        }
+        uint32_t *dst = reinterpret_cast<uint32_t *>(out + ((size_t)n * p.K + k) * oh * ow);
+        if (VARIANT == AGYM_OUT_RESIZE_FULL) {
+            resample_w<float>(bufA, rw, bufB, p.S_w, rh, flex_axis(p, 1, 2, rw, rw), tid, kThreads);
+            __syncthreads();
+            const AxisRef ah = flex_axis(p, 0, 2, rh, rh);
+            for (int t = tid; t < wpp; t += kThreads) {
+                const int y = fd_wpr.div(t), x0 = 4 * (t - y * wpr);
+                dst[t] = resample_h_word(bufB, p.S_w, ah, y, x0);
+            }
+        } else {
+            for (int t = tid; t < wpp; t += kThreads) {
+                const int y = fd_wpr.div(t), x0 = 4 * (t - y * wpr);
+                uint32_t word = 0u;
+                const int py = y - oy;
+                if (py >= 0 && py < rh) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int px = x0 + i - ox;
+                        if (px >= 0 && px < rw) word |= quant_u8(bufA[py * rw + px]) << (8 * i);
+                    }
+                }
+                dst[t] = word;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------ synth
+__global__ void k_synth(uint4 *dst, size_t n_vec, uint64_t seed) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n_vec; i += (size_t)gridDim.x * blockDim.x) {
+        uint64_t z = seed + i * 0x9E3779B97F4A7C15ull;
+        uint32_t o[4];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            z += 0x9E3779B97F4A7C15ull;
+            uint64_t x = z;
+            x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+            x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+            x ^= x >> 31;
+            o[2 * j] = (uint32_t)x; o[2 * j + 1] = (uint32_t)(x >> 32);
+        }
+        dst[i] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+}
+
+template <typename F>
+cudaError_t set_smem(F func, size_t bytes) {
+    if (bytes > 48 * 1024)
+        return cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    return cudaSuccess;
+}
+
+size_t a16(size_t v) { return (v + 15) & ~size_t(15); }
+
+}  // namespace
+
+// --------------------------------------------------------------------------- launchers
+cudaError_t launch_ingest_atari(const DevPlan &p, const uint8_t *fa, const uint8_t *fb, const uint8_t *flags,
+                                uint8_t *ring, int32_t *head, float *pcache, cudaStream_t st) {
+    size_t smem = a16(sizeof(int32_t) * 3 * (p.S_w + p.S_h)) + a16(2 * (size_t)2 * p.S_h * p.raw_w);
+    if (pcache) smem += a16(p.plane) + sizeof(float) * p.S_h * p.p_w;
+    cudaError_t e;
+    if (p.raw_c == 1) {
+        if ((e = set_smem(k_ingest_atari<1>, smem)) != cudaSuccess) return e;
+        k_ingest_atari<1><<<p.N, kThreads, smem, st>>>(p, fa, fb, flags, ring, head, pcache);
+    } else {
+        if ((e = set_smem(k_ingest_atari<3>, smem)) != cudaSuccess) return e;
+        k_ingest_atari<3><<<p.N, kThreads, smem, st>>>(p, fa, fb, flags, ring, head, pcache);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_ingest_dmc(const DevPlan &p, const uint8_t *f, const uint8_t *flags, uint8_t *ring, int32_t *head,
+                              float *pcache, cudaStream_t st) {
+    size_t smem = pcache ? a16(p.plane) + sizeof(float) * p.S_h * p.p_w : 0;
+    cudaError_t e;
+    if ((e = set_smem(k_ingest_dmc, smem)) != cudaSuccess) return e;
+    k_ingest_dmc<<<p.N, kThreads, smem, st>>>(p, f, flags, ring, head, pcache);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_stack(const DevPlan &p, const uint8_t *ring, const int32_t *head, uint8_t *out, cudaStream_t st) {
+    k_stack<<<p.N, kThreads, 0, st>>>(p, ring, head, out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_observe_fixed(const DevPlan &p, const uint8_t *ring, const int32_t *head, const double *action,
+                                 const uint8_t *ctrl, int32_t *loc, int variant, uint8_t *out, cudaStream_t st) {
+    cudaError_t e;
+    if (variant == AGYM_OUT_CROP) {
+        k_observe_fixed<AGYM_OUT_CROP><<<p.N, kThreads, 0, st>>>(p, ring, head, action, ctrl, loc, out);
+    } else if (variant == AGYM_OUT_MASK) {
+        k_observe_fixed<AGYM_OUT_MASK><<<p.N, kThreads, 0, st>>>(p, ring, head, action, ctrl, loc, out);
+    } else {
+        const size_t smem = sizeof(float) * ((size_t)p.f_h * p.f_w + (size_t)p.f_h * p.S_w);
+        if ((e = set_smem(k_observe_fixed<AGYM_OUT_RESIZE_FULL>, smem)) != cudaSuccess) return e;
+        k_observe_fixed<AGYM_OUT_RESIZE_FULL><<<p.N, kThreads, smem, st>>>(p, ring, head, action, ctrl, loc, out);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_observe_peripheral(const DevPlan &p, const uint8_t *ring, const int32_t *head, const float *pcache,
+                                      const double *action, const uint8_t *ctrl, int32_t *loc, uint8_t *out,
+                                      cudaStream_t st) {
+    const size_t smem = a16(p.plane) + sizeof(float) * ((size_t)p.S_h * p.p_w + (size_t)p.p_h * p.p_w + (size_t)p.p_h * p.S_w);
+    cudaError_t e;
+    if (pcache) {
+        if ((e = set_smem(k_observe_peripheral<true>, smem)) != cudaSuccess) return e;
+        k_observe_peripheral<true><<<p.N, kThreads, smem, st>>>(p, ring, head, pcache, action, ctrl, loc, out);
+    } else {
+        if ((e = set_smem(k_observe_peripheral<false>, smem)) != cudaSuccess) return e;
+        k_observe_peripheral<false><<<p.N, kThreads, smem, st>>>(p, ring, head, pcache, action, ctrl, loc, out);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_observe_flexible(const DevPlan &p, const uint8_t *ring, const int32_t *head, const double *action,
+                                    const int32_t *atype, const uint8_t *ctrl, int32_t *loc, int32_t *res, int variant,
+                                    int pad_h, int pad_w, uint8_t *out, cudaStream_t st) {
+    const size_t smem = sizeof(float) * 2 * (size_t)p.plane;
+    cudaError_t e;
+#define AGYM_LAUNCH_FLEX(V)                                                                              \
+    if ((e = set_smem(k_observe_flexible<V>, smem)) != cudaSuccess) return e;                            \
+    k_observe_flexible<V><<<p.N, kThreads, smem, st>>>(p, ring, head, action, atype, ctrl, loc, res, pad_h, pad_w, out);
+    if (variant == AGYM_OUT_CROP) { AGYM_LAUNCH_FLEX(AGYM_OUT_CROP) }
+    else if (variant == AGYM_OUT_MASK) { AGYM_LAUNCH_FLEX(AGYM_OUT_MASK) }
+    else { AGYM_LAUNCH_FLEX(AGYM_OUT_RESIZE_FULL) }
+#undef AGYM_LAUNCH_FLEX
+    return cudaGetLastError();
+}
+
+cudaError_t launch_synth(uint8_t *dst, size_t n, uint64_t seed, cudaStream_t st) {
+    const size_t n_vec = n / 16;
+    if (n_vec == 0) return cudaSuccess;
+    const int blocks = (int)((n_vec + 255) / 256 < 148 * 8 ? (n_vec + 255) / 256 : 148 * 8);
+    k_synth<<<blocks, 256, 0, st>>>(reinterpret_cast<uint4 *>(dst), n_vec, seed);
+    return cudaGetLastError();
+}
+
+}  // namespace agym

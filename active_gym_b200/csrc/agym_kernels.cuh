@@ -1,0 +1,57 @@
+// Device-side parameter blocks and launcher prototypes shared by agym_kernels.cu (device
+// code + launchers) and agym_abi.cu (plan management + the extern "C" surface).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace agym {
+
+// One antialiased-resample axis table inside the plan's device pool.
+struct AxisRef {
+    const int32_t *xmin;  // [n_out]
+    const float *w;       // [n_out][taps]
+    int32_t n_in, n_out, taps;
+};
+
+// Flexible fovea: per window size r (1..S) three tables per axis, stored as offsets (in
+// 32-bit words) into the pool so one small index array serves every env.
+struct FlexEntry {
+    int32_t xmin_off, w_off, taps, n_out;
+};
+
+struct DevPlan {
+    int32_t N, K, S_h, S_w, plane;      // plane = S_h * S_w
+    int32_t raw_h, raw_w, raw_c;
+    int32_t lw0, lw1, lw2;              // luma weights per channel position
+    int32_t f_h, f_w, p_h, p_w;
+    int32_t relative, init_r, init_c;
+    double lo, hi;
+    // cv2 bilinear raw -> obs (pool pointers)
+    const int32_t *cx_s0, *cx_s1, *cx_coef;   // [S_w]
+    const int32_t *cy_s0, *cy_s1, *cy_coef;   // [S_h]
+    // antialiased axes (n_in -> n_out)
+    AxisRef sq_w, sq_h;     // squeeze  S -> p      (fov_env.py:367)
+    AxisRef ex_w, ex_h;     // expand   p -> S      (fov_env.py:368)
+    AxisRef full_w, full_h; // resize_to_full f -> S (fov_env.py:120,182)
+    // flexible fovea tables: index [axis][family][r], family 0 = r->f, 1 = f->r, 2 = r->S
+    const FlexEntry *flex;  // [2][3][S_max+1]
+    const int32_t *pool_i;  // pool base viewed as int32
+    int32_t S_max;
+};
+
+cudaError_t launch_ingest_atari(const DevPlan &p, const uint8_t *fa, const uint8_t *fb, const uint8_t *flags,
+                                uint8_t *ring, int32_t *head, float *pcache, cudaStream_t st);
+cudaError_t launch_ingest_dmc(const DevPlan &p, const uint8_t *f, const uint8_t *flags, uint8_t *ring,
+                              int32_t *head, float *pcache, cudaStream_t st);
+cudaError_t launch_stack(const DevPlan &p, const uint8_t *ring, const int32_t *head, uint8_t *out, cudaStream_t st);
+cudaError_t launch_observe_fixed(const DevPlan &p, const uint8_t *ring, const int32_t *head, const double *action,
+                                 const uint8_t *ctrl, int32_t *loc, int variant, uint8_t *out, cudaStream_t st);
+cudaError_t launch_observe_peripheral(const DevPlan &p, const uint8_t *ring, const int32_t *head, const float *pcache,
+                                      const double *action, const uint8_t *ctrl, int32_t *loc, uint8_t *out,
+                                      cudaStream_t st);
+cudaError_t launch_observe_flexible(const DevPlan &p, const uint8_t *ring, const int32_t *head, const double *action,
+                                    const int32_t *atype, const uint8_t *ctrl, int32_t *loc, int32_t *res, int variant,
+                                    int pad_h, int pad_w, uint8_t *out, cudaStream_t st);
+cudaError_t launch_synth(uint8_t *dst, size_t n, uint64_t seed, cudaStream_t st);
+
+}  // namespace agym

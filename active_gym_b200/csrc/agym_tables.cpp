@@ -1,0 +1,89 @@
+// Host-side coefficient tables (see agym_tables.h).
+#include "agym_tables.h"
+
+#include <algorithm>
+#include <cmath>
+
+namespace agym {
+
+// OpenCV resize.cpp, INTER_LINEAR, 8-bit source: per destination index d the source position
+// is computed in double, narrowed to float, split into floor + fraction, and the fraction is
+// turned into two 11-bit weights with cvRound (round half to even).
+Cv2Axis build_cv2_axis(int n_src, int n_dst, bool zero_frac_at_border) {
+    Cv2Axis ax;
+    ax.s0.resize(n_dst); ax.s1.resize(n_dst); ax.coef.resize(n_dst);
+    const double inv_scale = static_cast<double>(n_dst) / static_cast<double>(n_src);
+    const double scale = 1.0 / inv_scale;
+    for (int d = 0; d < n_dst; ++d) {
+        float pos = static_cast<float>((d + 0.5) * scale - 0.5);
+        int s = static_cast<int>(std::floor(pos));
+        float frac = pos - static_cast<float>(s);
+        if (zero_frac_at_border) {
+            if (s < 0) { s = 0; frac = 0.f; }
+            if (s >= n_src - 1) { s = n_src - 1; frac = 0.f; }
+        }
+        const int c0 = static_cast<int>(std::lrintf((1.f - frac) * 2048.f));
+        const int c1 = static_cast<int>(std::lrintf(frac * 2048.f));
+        ax.s0[d] = std::min(std::max(s, 0), n_src - 1);
+        ax.s1[d] = std::min(std::max(s + 1, 0), n_src - 1);
+        ax.coef[d] = (c0 & 0xffff) | (c1 << 16);
+    }
+    return ax;
+}
+
+// ATen UpSampleKernel.cpp, _compute_indices_min_size_weights_aa with the bilinear (triangle)
+// filter, evaluated in double (the Atari reference path is float64).
+AaAxis build_aa_axis(int n_in, int n_out) {
+    AaAxis ax;
+    ax.n_in = n_in; ax.n_out = n_out;
+    ax.xmin.resize(n_out);
+    if (n_in == n_out) {  // ATen skips a pass whose size does not change
+        ax.taps = 1;
+        ax.w.assign(n_out, 1.0f);
+        for (int i = 0; i < n_out; ++i) ax.xmin[i] = i;
+        return ax;
+    }
+    const double scale = static_cast<double>(n_in) / static_cast<double>(n_out);
+    const double support = scale >= 1.0 ? scale : 1.0;
+    const double inv = scale >= 1.0 ? 1.0 / scale : 1.0;
+    const int max_taps = static_cast<int>(std::ceil(support)) * 2 + 1;
+    std::vector<int> xsize(n_out);
+    std::vector<double> wd(static_cast<size_t>(n_out) * max_taps, 0.0);
+    int taps = 1;
+    for (int i = 0; i < n_out; ++i) {
+        const double center = scale * (i + 0.5);
+        int lo = static_cast<int>(center - support + 0.5);
+        lo = std::max(lo, 0);
+        int hi = static_cast<int>(center + support + 0.5);
+        hi = std::min(hi, n_in);
+        int cnt = std::min(std::max(hi - lo, 0), max_taps);
+        double total = 0.0;
+        double *row = wd.data() + static_cast<size_t>(i) * max_taps;
+        for (int j = 0; j < cnt; ++j) {
+            const double x = std::fabs((j + lo - center + 0.5) * inv);
+            row[j] = x < 1.0 ? 1.0 - x : 0.0;
+            total += row[j];
+        }
+        if (total != 0.0)
+            for (int j = 0; j < cnt; ++j) row[j] /= total;
+        // drop exact-zero tails so the device loop is as short as the filter really is
+        while (cnt > 1 && row[cnt - 1] == 0.0) --cnt;
+        ax.xmin[i] = lo; xsize[i] = cnt;
+        taps = std::max(taps, cnt);
+    }
+    taps = std::min(taps, n_in);
+    ax.taps = taps;
+    ax.w.assign(static_cast<size_t>(n_out) * taps, 0.f);
+    for (int i = 0; i < n_out; ++i) {
+        const double *row = wd.data() + static_cast<size_t>(i) * max_taps;
+        int lo = ax.xmin[i];
+        int shift = 0;  // keep lo + taps <= n_in: move the window left, pad zeros in front
+        if (lo + taps > n_in) { shift = lo + taps - n_in; lo -= shift; }
+        for (int j = 0; j < xsize[i] && j + shift < taps; ++j)
+            ax.w[static_cast<size_t>(i) * taps + j + shift] = static_cast<float>(row[j]);
+        ax.xmin[i] = lo;
+    }
+    return ax;
+}
+
+}  // namespace agym

@@ -1,0 +1,34 @@
+// Host-side coefficient tables for the observation kernels.
+//
+// Everything a kernel multiplies a pixel by is computed here, on the host, once per plan,
+// with the same scalar arithmetic the reference's libraries use, so that no device float op
+// takes part in coefficient generation:
+//   * Cv2Axis  — OpenCV's INTER_LINEAR 11-bit fixed-point coefficients, the resize behind
+//                AtariEnv._get_state (atari_env.py:74).
+//   * AaAxis   — ATen's antialiased-bilinear (triangle filter) weights, the resample behind
+//                torchvision Resize in the foveal wrappers (fov_env.py:120,248,278,366-368).
+#pragma once
+#include <cstdint>
+#include <vector>
+
+namespace agym {
+
+// One axis of cv2.resize(INTER_LINEAR) on 8-bit data.
+struct Cv2Axis {
+    std::vector<int32_t> s0, s1;   // the two source indices per destination index (clamped)
+    std::vector<int32_t> coef;     // c0 | (c1 << 16), each an 11-bit fixed-point weight
+};
+// `zero_frac_at_border`: OpenCV zeroes the fraction at the borders on the x axis only.
+Cv2Axis build_cv2_axis(int n_src, int n_dst, bool zero_frac_at_border);
+
+// One axis of an antialiased bilinear resample n_in -> n_out.  Every destination index reads
+// `taps` consecutive sources starting at xmin[i]; rows are zero-padded and, near the right
+// border, shifted left so that xmin[i] + taps <= n_in always holds (no bounds checks on device).
+struct AaAxis {
+    int n_in = 0, n_out = 0, taps = 0;
+    std::vector<int32_t> xmin;     // [n_out]
+    std::vector<float> w;          // [n_out][taps]
+};
+AaAxis build_aa_axis(int n_in, int n_out);
+
+}  // namespace agym

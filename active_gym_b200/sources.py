@@ -1,0 +1,246 @@
+"""Frame sources: the seam BELOW the observation path.
+
+The simulators stay on the host (``BASELINE.json:north_star``): ALE and MuJoCo step per env on
+CPU cores and hand batched raw frames to the GPU through pinned staging buffers.  A source
+produces, per call, exactly what the kernels consume: raw frames + per-env ingest flags, and
+the simulator-side scalars (reward, done).
+
+* ``ALEPool``      — N ``atari_py.ALEInterface`` objects driven with the reference's simulator-side
+                     logic: no-op + fire reset, action repeat with frames taken at t==2/t==3,
+                     episodic-life termination (atari_env.py:84-108, 123-131, 135-140).
+* ``DMCPool``      — N ``dm_control`` tasks (dmc_env.py:100-106, 166-173, 202-224).
+* ``SyntheticAtariSource`` / ``SyntheticDMCSource`` — device-generated frames for benchmarks.
+"""
+from __future__ import annotations
+
+import random
+from typing import Callable, Optional, Sequence
+
+import numpy as np
+import torch
+
+from ._lib import FLAG_FRAME_A, FLAG_FRAME_B, FLAG_HARD_RESET, FLAG_IDLE
+
+
+def _pinned(shape, dtype=torch.uint8) -> torch.Tensor:
+    t = torch.zeros(shape, dtype=dtype)
+    if torch.cuda.is_available():
+        t = t.pin_memory()
+    return t
+
+
+class ALEPool:
+    """Host pool of Arcade Learning Environment instances (the L0 simulators of SURVEY.md §1)."""
+
+    raw_shape = (210, 160, 1)
+
+    def __init__(self, args, num_envs: int, ale_factory: Optional[Callable[[int], object]] = None):
+        self.num_envs = int(num_envs)
+        self.action_repeat = int(args.action_repeat)
+        self.training = True
+        if ale_factory is None:
+            import atari_py  # third-party; absent in this image
+
+            def ale_factory(i):  # atari_env.py:44-50
+                ale = atari_py.ALEInterface()
+                ale.setInt("random_seed", args.seed + i)
+                ale.setInt("max_num_frames_per_episode", int(args.max_episode_length))
+                ale.setFloat("repeat_action_probability", 0)
+                ale.setInt("frame_skip", 0)
+                ale.setBool("color_averaging", False)
+                ale.loadROM(atari_py.get_game_path(args.game))
+                return ale
+        self.ales = [ale_factory(i) for i in range(self.num_envs)]
+        actions = self.ales[0].getMinimalActionSet()
+        self.actions = dict(enumerate(actions))  # atari_env.py:51-52
+        self.n_actions = len(actions)
+        self.lives = [0] * self.num_envs
+        self.life_termination = [False] * self.num_envs
+        n = self.num_envs
+        self.frames_a, self.frames_b = _pinned((n, 210, 160)), _pinned((n, 210, 160))
+        self._fa, self._fb = self.frames_a.numpy(), self.frames_b.numpy()
+        self.flags = np.zeros(n, np.uint8)
+
+    def _screen(self, ale, dst):
+        g = ale.getScreenGrayscale()
+        dst[...] = np.asarray(g).reshape(210, 160)
+
+    def reset(self, mask: Optional[np.ndarray] = None):
+        """atari_env.py:84-113 minus the buffer work.  Returns (frames, frames, flags)."""
+        for i, ale in enumerate(self.ales):
+            if mask is not None and not mask[i]:
+                self.flags[i] = FLAG_IDLE
+                continue
+            if self.life_termination[i]:
+                self.life_termination[i] = False
+                ale.act(0)
+                self.flags[i] = FLAG_FRAME_A
+            else:
+                ale.reset_game()
+                for _ in range(random.randrange(30)):
+                    ale.act(0)
+                    if ale.game_over():
+                        ale.reset_game()
+                self.flags[i] = FLAG_FRAME_A | FLAG_HARD_RESET
+            if self.n_actions >= 3:
+                ale.act(1)
+                if ale.game_over():
+                    ale.reset_game()
+                    ale.act(2)
+                if ale.game_over():
+                    ale.reset_game()
+            self._screen(ale, self._fa[i])
+            self.lives[i] = ale.lives()
+        return self.frames_a, self.frames_a, self.flags
+
+    def step(self, motor_action: Sequence[int]):
+        """atari_env.py:119-140 minus the buffer work.  Returns (fa, fb, flags, reward, done)."""
+        n = self.num_envs
+        reward, done = np.zeros(n, np.float64), np.zeros(n, bool)
+        motor_action = np.asarray(motor_action).reshape(n)
+        for i, ale in enumerate(self.ales):
+            fl, r, d = 0, 0, False
+            for t in range(self.action_repeat):
+                r += ale.act(self.actions.get(int(motor_action[i])))
+                if t == 2:
+                    self._screen(ale, self._fa[i]); fl |= FLAG_FRAME_A
+                elif t == 3:
+                    self._screen(ale, self._fb[i]); fl |= FLAG_FRAME_B
+                d = ale.game_over()
+                if d:
+                    break
+            if self.training:
+                lives = ale.lives()
+                if lives < self.lives[i] and lives > 0:
+                    self.life_termination[i] = not d
+                    d = True
+                self.lives[i] = lives
+            self.flags[i], reward[i], done[i] = fl, r, d
+        return self.frames_a, self.frames_b, self.flags, reward, done
+
+
+class DMCPool:
+    """Host pool of dm_control tasks; renders at obs_size (dmc_env.py:175-180)."""
+
+    def __init__(self, args, num_envs: int, env_factory: Optional[Callable[[int], object]] = None):
+        self.num_envs, self.action_repeat = int(num_envs), int(args.action_repeat)
+        self.obs_size, self.camera_id = tuple(args.obs_size), args.camera_id
+        if env_factory is None:
+            from dm_control import suite  # third-party; absent in this image
+
+            def env_factory(i):  # dmc_env.py:92-106
+                kw = dict(args.task_kwargs); kw["random"] = args.seed + i
+                return suite.load(domain_name=args.domain_name, task_name=args.task_name, task_kwargs=kw,
+                                  visualize_reward=args.visualize_reward, environment_kwargs=args.environment_kwargs)
+        self.envs = [env_factory(i) for i in range(self.num_envs)]
+        spec = self.envs[0].action_spec()
+        self.true_low = np.asarray(spec.minimum, np.float32) + np.zeros(spec.shape, np.float32)
+        self.true_high = np.asarray(spec.maximum, np.float32) + np.zeros(spec.shape, np.float32)
+        h, w = self.obs_size
+        self.raw_shape = (h, w, 3)
+        self.frames = _pinned((self.num_envs, h, w, 3))
+        self._f = self.frames.numpy()
+        self.flags = np.zeros(self.num_envs, np.uint8)
+        self.last_time_steps = [None] * self.num_envs
+
+    def _convert_action(self, a):  # dmc_env.py:166-173, norm space is [-1, 1]
+        a = a.astype(np.float64)
+        a = (a - (-1.0)) / 2.0
+        return (a * (self.true_high - self.true_low) + self.true_low).astype(np.float32)
+
+    def _render(self, i):
+        h, w = self.obs_size
+        self._f[i] = self.envs[i].physics.render(height=h, width=w, camera_id=self.camera_id)
+
+    def reset(self, mask=None):
+        for i, env in enumerate(self.envs):
+            if mask is not None and not mask[i]:
+                self.flags[i] = FLAG_IDLE
+                continue
+            self.last_time_steps[i] = env.reset()
+            self._render(i)
+            self.flags[i] = FLAG_FRAME_A | FLAG_HARD_RESET
+        return self.frames, self.flags
+
+    def step(self, motor_action):
+        n = self.num_envs
+        reward, done = np.zeros(n, np.float64), np.zeros(n, bool)
+        motor_action = np.asarray(motor_action, np.float32).reshape(n, -1)
+        for i, env in enumerate(self.envs):
+            a = self._convert_action(motor_action[i])
+            r = 0
+            for _ in range(self.action_repeat):  # dmc_env.py:218-223
+                ts = env.step(a)
+                r += ts.reward or 0
+                if ts.last():
+                    done[i] = True
+                    break
+            self.last_time_steps[i] = ts
+            self._render(i)
+            reward[i], self.flags[i] = r, FLAG_FRAME_A
+        return self.frames, self.flags, reward, done
+
+
+class SyntheticAtariSource:
+    """Frames generated on the device (or given as a pool of pre-generated batches): the
+    benchmark / test stand-in for ``ALEPool``.  Never terminates; reward is 0."""
+
+    def __init__(self, num_envs: int, channels: int = 1, device=None, pool: int = 4, seed: int = 1234):
+        self.num_envs, self.n_actions = int(num_envs), 18
+        self.raw_shape = (210, 160, channels)
+        self.device = torch.device(device if device is not None else "cuda")
+        shape = (num_envs, 210, 160) if channels == 1 else (num_envs, 210, 160, 3)
+        g = torch.Generator(device=self.device).manual_seed(seed)
+        self.batches = [torch.randint(0, 256, shape, dtype=torch.uint8, device=self.device, generator=g)
+                        for _ in range(max(2, pool))]
+        self.t = 0
+        self.flags_step = torch.full((num_envs,), FLAG_FRAME_A | FLAG_FRAME_B, dtype=torch.uint8, device=self.device)
+        self.flags_reset = torch.full((num_envs,), FLAG_FRAME_A | FLAG_HARD_RESET, dtype=torch.uint8, device=self.device)
+        self._zero = np.zeros(num_envs)
+        self._false = np.zeros(num_envs, bool)
+
+    def _next(self):
+        b = self.batches[self.t % len(self.batches)]
+        self.t += 1
+        return b
+
+    def reset(self, mask=None):
+        f = self._next()
+        flags = self.flags_reset
+        if mask is not None:
+            m = torch.as_tensor(np.asarray(mask, bool), device=self.device)
+            flags = torch.where(m, flags, torch.full_like(flags, FLAG_IDLE))
+        return f, f, flags
+
+    def step(self, motor_action):
+        return self._next(), self._next(), self.flags_step, self._zero, self._false
+
+
+class SyntheticDMCSource:
+    def __init__(self, num_envs: int, obs_size=(84, 84), device=None, pool: int = 4, seed: int = 1234, action_dim: int = 2):
+        self.num_envs, self.action_dim = int(num_envs), action_dim
+        self.raw_shape = (obs_size[0], obs_size[1], 3)
+        self.device = torch.device(device if device is not None else "cuda")
+        g = torch.Generator(device=self.device).manual_seed(seed)
+        self.batches = [torch.randint(0, 256, (num_envs,) + self.raw_shape, dtype=torch.uint8, device=self.device, generator=g)
+                        for _ in range(max(2, pool))]
+        self.t = 0
+        self.flags_step = torch.full((num_envs,), FLAG_FRAME_A, dtype=torch.uint8, device=self.device)
+        self.flags_reset = torch.full((num_envs,), FLAG_FRAME_A | FLAG_HARD_RESET, dtype=torch.uint8, device=self.device)
+        self.true_low, self.true_high = -np.ones(action_dim, np.float32), np.ones(action_dim, np.float32)
+        self._zero, self._false = np.zeros(num_envs), np.zeros(num_envs, bool)
+
+    def _next(self):
+        b = self.batches[self.t % len(self.batches)]
+        self.t += 1
+        return b
+
+    def reset(self, mask=None):
+        flags = self.flags_reset
+        if mask is not None:
+            m = torch.as_tensor(np.asarray(mask, bool), device=self.device)
+            flags = torch.where(m, flags, torch.full_like(flags, FLAG_IDLE))
+        return self._next(), flags
+
+    def step(self, motor_action):
+        return self._next(), self.flags_step, self._zero, self._false

@@ -1,0 +1,149 @@
+/*
+ * agym_b200.h — C ABI of the B200-native active-perception observation path.
+ *
+ * This is the drop-in boundary for the observation code of elicassion/active-gym
+ * (reference files cited as <file>:<lines> relative to /root/reference/active_gym/).
+ * The reference has no FFI layer of its own (it is pure Python calling numpy / OpenCV /
+ * torchvision per environment), so each entry point below names the reference METHOD it
+ * replaces; INTEGRATION.md shows the ctypes stub a maintainer would put into those methods.
+ *
+ * Conventions
+ *   - plain C, no torch / C++ types; every function returns 0 (AGYM_OK) or a negative
+ *     agym_status, or a positive cudaError_t from the launch; nothing throws or exits.
+ *   - the caller owns every buffer passed in.  `d_` parameters are DEVICE pointers on the current device,
+ *     `h_` parameters are HOST pointers.  A plan owns only its small coefficient tables.
+ *   - all device work is enqueued on `stream` (a cudaStream_t passed as void*); no
+ *     function synchronises unless its name ends in `_host`.
+ *   - u8 pixels everywhere: the reference's normalised float value is
+ *     float64(float32(u)/255) for the u8 value u.
+ *
+ * Data layout in HBM (N = envs, K = frame_stack, S = obs_size, f = fov_size)
+ *   ring  u8  [N][K][S_h][S_w]  frame stack; slot head[n] holds the NEWEST frame, logical
+ *                               order oldest->newest is (head+1)%K ... head
+ *   head  i32 [N]
+ *   loc   i32 [N][2]            (row, col) of the fovea's upper-left corner
+ *   res   i32 [N][2]            (rows, cols) of the flexible fovea
+ *   pcache f32 [N][K][p_h][p_w] optional cache of each ring slot's peripheral squeeze
+ */
+#ifndef AGYM_B200_H
+#define AGYM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AGYM_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define AGYM_API __attribute__((visibility("default")))
+#else
+#define AGYM_API
+#endif
+
+typedef enum agym_status {
+    AGYM_OK = 0,
+    AGYM_ERR_INVALID_ARG = -1,   /* null pointer, non-positive size, fov >= obs ... */
+    AGYM_ERR_UNSUPPORTED = -2,   /* geometry outside what the kernels are built for */
+    AGYM_ERR_NO_DEVICE = -3,     /* no CUDA device / not an sm_100 part */
+    AGYM_ERR_ALLOC = -4
+} agym_status;
+
+/* per-env ingest flags (u8) */
+#define AGYM_FLAG_FRAME_A 1u     /* frame A is valid   (atari_env.py:125-126, t == 2)        */
+#define AGYM_FLAG_FRAME_B 2u     /* frame B is valid   (atari_env.py:127-128, t == 3)        */
+#define AGYM_FLAG_HARD_RESET 4u  /* zero-fill the stack first (atari_env.py:80-82,91)        */
+#define AGYM_FLAG_IDLE 8u        /* env does not push a frame in this call                    */
+
+/* per-env fovea control (u8), optional (NULL = AGYM_FOV_APPLY for every env) */
+#define AGYM_FOV_APPLY 0u        /* apply the sensory action (fov_env.py:187-203)             */
+#define AGYM_FOV_RESET 1u        /* loc = rint(fov_init_loc), res = fov_size (fov_env.py:149-150,250-251) */
+#define AGYM_FOV_KEEP 2u         /* leave loc / res unchanged                                 */
+
+/* output variants of the observe calls (fov_env.py:176-183, 289-296) */
+#define AGYM_OUT_CROP 0          /* (K, f_h, f_w); flexible: padded (K, pad_h, pad_w)         */
+#define AGYM_OUT_MASK 1          /* mask_out: (K, S_h, S_w), zero outside the fovea           */
+#define AGYM_OUT_RESIZE_FULL 2   /* resize_to_full: (K, S_h, S_w)                             */
+
+/* sensory_action_type of the flexible fovea (fov_env.py:236-238) */
+#define AGYM_ATYPE_FOV_LOC 0
+#define AGYM_ATYPE_FOV_RES 1
+
+/* Static configuration of one env batch: the fields of AtariEnvArgs / DMCEnvArgs that the
+ * observation path reads (atari_env.py:25-39, dmc_env.py:56-76, fov_env.py:110-122,365). */
+typedef struct agym_config {
+    int32_t n_envs;              /* N                                                          */
+    int32_t frame_stack;         /* K            (atari_env.py:55, dmc_env.py:90)              */
+    int32_t obs_h, obs_w;        /* obs_size     (atari_env.py:59)                             */
+    int32_t raw_h, raw_w, raw_c; /* simulator frame: Atari 210x160x{1 gray,3 RGB}; DMC obs x3  */
+    int32_t luma_w[3];           /* 15-bit luma weight per channel position, when raw_c == 3   */
+    int32_t fov_h, fov_w;        /* fov_size     (fov_env.py:110); 0 = no fovea (base env)     */
+    int32_t periph_h, periph_w;  /* peripheral_res (fov_env.py:365); 0 = none                  */
+    int32_t relative;            /* sensory_action_mode == "relative" (fov_env.py:114-118)     */
+    double act_lo, act_hi;       /* sensory_action_space, relative mode (fov_env.py:116,170)   */
+    double fov_init_loc[2];      /* fov_init_loc (fov_env.py:111,149-150)                      */
+} agym_config;
+
+typedef struct agym_plan agym_plan;   /* opaque: validated config + device coefficient tables */
+
+AGYM_API int agym_abi_version(void);
+AGYM_API const char *agym_status_string(int status);
+
+/* Builds the coefficient tables on the host (OpenCV's 11-bit bilinear coefficients for
+ * raw->obs, ATen's antialiased-bilinear weights for every resample the wrappers perform),
+ * uploads them to the current device and returns a plan. */
+AGYM_API int agym_plan_create(const agym_config *cfg, agym_plan **out_plan);
+AGYM_API int agym_plan_destroy(agym_plan *plan);
+/* sizes the caller needs to allocate (bytes) */
+AGYM_API size_t agym_plan_ring_bytes(const agym_plan *plan);
+AGYM_API size_t agym_plan_pcache_bytes(const agym_plan *plan);
+
+/* Replaces AtariEnv._get_state + the frame logic of _step/_reset (atari_env.py:73-75,
+ * 80-82, 91, 111-114, 121-133): per env gray(A),gray(B) -> cv2 INTER_LINEAR resize to
+ * obs_size -> max -> push into the ring.  d_frames_a / d_frames_b: u8 [N][raw_h][raw_w][raw_c].
+ * d_pcache (may be NULL): also refresh the pushed slot's peripheral squeeze cache. */
+AGYM_API int agym_ingest_atari(const agym_plan *plan, const uint8_t *d_frames_a, const uint8_t *d_frames_b,
+                      const uint8_t *d_flags, uint8_t *d_ring, int32_t *d_head, float *d_pcache,
+                      void *stream);
+
+/* Replaces DMCEnv._get_obs (pixel, grey branch) + stack logic (dmc_env.py:175-183, 193-195,
+ * 206-207, 228-230): luma of the rendered frame -> push.  d_frames: u8 [N][S_h][S_w][3]. */
+AGYM_API int agym_ingest_dmc(const agym_plan *plan, const uint8_t *d_frames, const uint8_t *d_flags,
+                    uint8_t *d_ring, int32_t *d_head, float *d_pcache, void *stream);
+
+/* Replaces np.stack(state_buffer) (atari_env.py:143, dmc_env.py:230): the base env's
+ * observation, oldest -> newest.  d_out: u8 [N][K][S_h][S_w]. */
+AGYM_API int agym_stack(const agym_plan *plan, const uint8_t *d_ring, const int32_t *d_head, uint8_t *d_out,
+               void *stream);
+
+/* Replaces FixedFovealEnv._fov_step + _get_fov_state (fov_env.py:166-203): updates d_loc
+ * from the sensory action (f64 [N][2]; may be NULL when every env is RESET/KEEP) and writes
+ * the observation.  d_out: u8 [N][K][f_h][f_w] (CROP) or [N][K][S_h][S_w] (MASK, RESIZE_FULL). */
+AGYM_API int agym_observe_fixed(const agym_plan *plan, const uint8_t *d_ring, const int32_t *d_head,
+                       const double *d_action, const uint8_t *d_fov_ctrl, int32_t *d_loc,
+                       int variant, uint8_t *d_out, void *stream);
+
+/* Replaces FixedFovealPeripheralEnv._get_fov_state (fov_env.py:375-388) with the loc update
+ * fused in.  d_pcache may be NULL (the squeeze is then recomputed from the ring).
+ * d_out: u8 [N][K][S_h][S_w]. */
+AGYM_API int agym_observe_peripheral(const agym_plan *plan, const uint8_t *d_ring, const int32_t *d_head,
+                            const float *d_pcache, const double *d_action, const uint8_t *d_fov_ctrl,
+                            int32_t *d_loc, uint8_t *d_out, void *stream);
+
+/* Replaces FlexibleFovealEnv._fov_step + _get_fov_state (fov_env.py:270-330).
+ * d_atype: i32 [N] (NULL = all FOV_LOC).  CROP writes the variable-size patch into the
+ * top-left corner of a zeroed [N][K][pad_h][pad_w] buffer (pad >= the largest res). */
+AGYM_API int agym_observe_flexible(const agym_plan *plan, const uint8_t *d_ring, const int32_t *d_head,
+                          const double *d_action, const int32_t *d_atype, const uint8_t *d_fov_ctrl,
+                          int32_t *d_loc, int32_t *d_res, int variant, int pad_h, int pad_w,
+                          uint8_t *d_out, void *stream);
+
+/* Benchmark / test helper: fills d_dst with a counter-based hash of (seed, byte index). */
+AGYM_API int agym_synth_frames(uint8_t *d_dst, size_t n_bytes, uint64_t seed, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AGYM_B200_H */
