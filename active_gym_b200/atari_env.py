@@ -1,0 +1,139 @@
+"""Atari base env: ``AtariEnvArgs``, the batched ``AtariVecEnv`` and the factory functions.
+
+Mirrors ``active_gym/atari_env.py`` of the reference (file:line citations refer to it).  The
+simulator part (ALE stepping, no-op / fire reset, episodic life) lives in a host-side frame
+source (``sources.ALEPool``); everything from the raw screen to the stacked observation runs
+on the GPU through ``ObservationPath``.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from .engine import LUMA_RGB, ObservationPath
+from .spaces import Box, Discrete, Env
+
+
+class AtariEnvArgs:
+    """Source-compatible with atari_env.py:25-39; adds defaults for the attributes the reference's
+    wrappers require but do not default (README quick-start raises AttributeError without them)."""
+
+    def __init__(self, game, seed, obs_size: Tuple[int, int], **kwargs):
+        self.env_backend = "atari_py"
+        self.device = None
+        self.seed = seed
+        self.max_episode_length = 108e3
+        self.game = game
+        self.frame_stack = 4
+        self.action_repeat = 4
+        self.obs_size = obs_size
+        self.mask_out = False
+        self.record = False
+        self.clip_reward = False
+        self.resize_to_full = False  # superset: no default in the reference (fov_env.py:120)
+        for k, v in kwargs.items():
+            self.__setattr__(k, v)
+
+
+def _path_from_args(args, num_envs, raw_shape, luma, device) -> ObservationPath:
+    fov = getattr(args, "fov_size", None)
+    return ObservationPath(
+        num_envs, args.frame_stack, tuple(args.obs_size), raw_shape, luma=luma,
+        fov_size=tuple(fov) if fov is not None else None,
+        fov_init_loc=getattr(args, "fov_init_loc", (0, 0)),
+        sensory_action_mode=getattr(args, "sensory_action_mode", "absolute"),
+        sensory_action_space=getattr(args, "sensory_action_space", (0.0, 0.0)),
+        peripheral_res=getattr(args, "peripheral_res", None), device=device,
+        cache_peripheral=getattr(args, "cache_peripheral", True))
+
+
+class AtariVecEnv(Env):
+    """N Atari environments; observation = (N, K, S_h, S_w) uint8 CUDA tensor.
+
+    Replaces AtariEnv (atari_env.py:41-172) for a batch.  ``source`` supplies the simulators
+    (default ``ALEPool`` when atari_py is importable).  The reference returns normalised
+    float64 = float32(u8)/255; values are identical after that conversion.
+    """
+
+    def __init__(self, args, num_envs: int = 1, source=None, device=None):
+        self.args = args
+        self.num_envs = int(num_envs)
+        self.frame_stack = args.frame_stack
+        self.action_repeat = args.action_repeat
+        self.obs_size = tuple(args.obs_size)
+        self.clip_reward = args.clip_reward
+        self.training = True
+        if source is None:
+            from .sources import ALEPool
+            source = ALEPool(args, self.num_envs)
+        self.source = source
+        self.path = _path_from_args(args, self.num_envs, tuple(source.raw_shape),
+                                    getattr(args, "luma", LUMA_RGB), device or getattr(args, "device", None))
+        self.device = self.path.device
+        self.action_space = Discrete(source.n_actions)
+        self.observation_space = Box(low=-1., high=1., shape=(self.frame_stack,) + self.obs_size, dtype=np.float32)
+        self.reward_range = (-float("inf"), float("inf"))
+
+    def _info(self, raw_reward):
+        return {"raw_reward": raw_reward}  # atari_env.py:77-78
+
+    def reset(self, seed=None, options=None, mask=None, return_state=True):
+        """atari_env.py:84-117.  ``mask`` (N,) bool selects the envs to reset (default: all)."""
+        fa, fb, flags = self.source.reset(mask)
+        self.path.ingest_atari(fa, fb, flags)
+        state = self.path.stack() if return_state else None
+        return state, self._info(np.zeros(self.num_envs))
+
+    def step(self, action, return_state=True):
+        """atari_env.py:119-148."""
+        fa, fb, flags, reward, done = self.source.step(action)
+        self.path.ingest_atari(fa, fb, flags)
+        state = self.path.stack() if return_state else None
+        return_reward = np.sign(reward) if self.clip_reward else reward
+        truncated = np.zeros(self.num_envs, bool)
+        return state, return_reward, done, truncated, self._info(reward)
+
+    def train(self):  # atari_env.py:158-159
+        self.training = True
+        if hasattr(self.source, "training"):
+            self.source.training = True
+
+    def eval(self):  # atari_env.py:162-163
+        self.training = False
+        if hasattr(self.source, "training"):
+            self.source.training = False
+
+    def render(self, mode="rgb_array", obs_size=None):
+        raise NotImplementedError("recording/rendering is outside the observation hot path (SURVEY.md §2 row 2)")
+
+    def close(self):
+        pass
+
+
+# ---- factories: atari_env.py:174-192, batched.  num_envs=1 + as_reference=True gives the single-env
+# drop-in whose reset()/step() return reference-typed values (see fov_env.SingleEnvAdapter).
+def AtariBaseEnv(args, num_envs: Optional[int] = None, source=None, device=None):
+    from .fov_env import RecordWrapper, SingleEnvAdapter
+    env = RecordWrapper(AtariVecEnv(args, num_envs or 1, source, device), args)
+    return SingleEnvAdapter(env) if num_envs is None else env
+
+
+def AtariFixedFovealEnv(args, num_envs: Optional[int] = None, source=None, device=None):
+    from .fov_env import FixedFovealEnv, SingleEnvAdapter
+    env = FixedFovealEnv(AtariBaseEnv(args, num_envs or 1, source, device), args)
+    return SingleEnvAdapter(env) if num_envs is None else env
+
+
+def AtariFlexibleFovealEnv(args, num_envs: Optional[int] = None, source=None, device=None):
+    from .fov_env import FlexibleFovealEnv, SingleEnvAdapter
+    env = FlexibleFovealEnv(AtariBaseEnv(args, num_envs or 1, source, device), args)
+    return SingleEnvAdapter(env) if num_envs is None else env
+
+
+def AtariFixedFovealPeripheralEnv(args, num_envs: Optional[int] = None, source=None, device=None):
+    from .fov_env import FixedFovealPeripheralEnv, SingleEnvAdapter
+    env = FixedFovealPeripheralEnv(AtariBaseEnv(args, num_envs or 1, source, device), args)
+    return SingleEnvAdapter(env) if num_envs is None else env

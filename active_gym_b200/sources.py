@@ -162,6 +162,11 @@ class DMCPool:
             self.flags[i] = FLAG_FRAME_A | FLAG_HARD_RESET
         return self.frames, self.flags
 
+    def extra_info(self):
+        """dmc_env.py:188-191: MuJoCo state and discount ride along in ``info``."""
+        return {"internal_state": np.stack([np.asarray(e.physics.get_state()).copy() for e in self.envs]),
+                "discount": np.array([getattr(ts, "discount", None) for ts in self.last_time_steps], dtype=object)}
+
     def step(self, motor_action):
         n = self.num_envs
         reward, done = np.zeros(n, np.float64), np.zeros(n, bool)

@@ -139,7 +139,8 @@ def run_atari(name, atari, screens, cls, *, mode, variant="crop", K=4, fov=(30, 
     meta = dict(kind="atari", env=cls.__name__, mode=mode, variant=variant, frame_stack=K, obs_size=(84, 84),
                 fov_size=fov, fov_init_loc=init, action_repeat=action_repeat, peripheral_res=periph,
                 lo=-10.0, hi=10.0, exact=exact, flexible=flexible, ragged=(flexible and variant == "crop"),
-                float32_from_call=None)
+                script=dict(game_over_at=list(game_over_at), lives_at={str(k): v for k, v in (lives_at or {}).items()}),
+                random_seed=7, training=training, tensor_actions=tensor_actions)
     rec = Recorder(meta)
     random.seed(7)
 
