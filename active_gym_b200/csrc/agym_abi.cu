@@ -144,6 +144,68 @@ int agym_plan_create(const agym_config *cfg, agym_plan **out_plan) {
         o_flex = pool.add_i(index);
     }
 
+    // ---- fast-path tables (see DevPlan)
+    // ingest: dp2a form of the horizontal pass, two output columns per thread
+    bool fast_ingest = (c.obs_w % 2 == 0) && (c.obs_w / 2 <= 256);
+    std::vector<int32_t> pair_tab, ybs_tab;
+    for (int x0 = 0; fast_ingest && x0 < c.obs_w; x0 += 2) {
+        const int s[4] = {cx.s0[x0], cx.s1[x0], cx.s0[x0 + 1], cx.s1[x0 + 1]};
+        const int base = s[0] & ~3;
+        int sel = 0;
+        for (int k = 0; k < 4; ++k) {
+            const int o = s[k] - base;
+            if (o < 0 || o > 7) fast_ingest = false;
+            sel |= (o & 7) << (4 * k);
+        }
+        pair_tab.insert(pair_tab.end(), {base, sel, cx.coef[x0], cx.coef[x0 + 1]});
+    }
+    for (int y = 0; y < c.obs_h; ++y) {
+        ybs_tab.push_back((cy.coef[y] & 0xffff) << 16);
+        ybs_tab.push_back((cy.coef[y] >> 16) << 16);
+    }
+    size_t o_pair = 0, o_ybs = 0;
+    if (fast_ingest) { o_pair = pool.add_i(pair_tab); o_ybs = pool.add_i(ybs_tab); }
+    // squeeze along W straight from u8 rows: a 16-byte window per output column
+    bool fast_squeeze = c.periph_h > 0;
+    size_t o_sqofs = 0, o_sqw = 0;
+    int sq_taps4 = 0;
+    if (fast_squeeze) {
+        const AaAxis ax = build_aa_axis(c.obs_w, c.periph_w);
+        sq_taps4 = (ax.taps + 3) & ~3;
+        std::vector<int32_t> ofs;
+        std::vector<float> wts(static_cast<size_t>(ax.n_out) * sq_taps4, 0.f);
+        for (int i = 0; i < ax.n_out; ++i) {
+            if ((ax.xmin[i] & 3) + ax.taps > 16) fast_squeeze = false;
+            ofs.push_back(ax.xmin[i] & ~3);
+            ofs.push_back(8 * (ax.xmin[i] & 3));
+            for (int j = 0; j < ax.taps; ++j) wts[static_cast<size_t>(i) * sq_taps4 + j] = ax.w[static_cast<size_t>(i) * ax.taps + j];
+        }
+        if (fast_squeeze) { o_sqofs = pool.add_i(ofs); o_sqw = pool.add_f(wts); }
+    }
+    // expand p -> S as two-tap lerps (plain bilinear upsampling: antialiasing is inactive)
+    bool fast_expand = c.periph_h > 0 && c.periph_h < c.obs_h && c.periph_w < c.obs_w && c.periph_h >= 2 && c.periph_w >= 2;
+    size_t o_ewi = 0, o_eww = 0, o_ehi = 0, o_ehw = 0;
+    if (fast_expand) {
+        auto lerp = [&](int n_in, int n_out, std::vector<int32_t> &i0, std::vector<float> &w0) {
+            const AaAxis ax = build_aa_axis(n_in, n_out);
+            for (int i = 0; i < n_out; ++i) {
+                int first = -1, last = -1;
+                for (int j = 0; j < ax.taps; ++j)
+                    if (ax.w[static_cast<size_t>(i) * ax.taps + j] != 0.f) { if (first < 0) first = j; last = j; }
+                if (first < 0 || last - first > 1) { fast_expand = false; return; }
+                const int a = ax.xmin[i] + first;
+                if (last > first) { i0.push_back(a); w0.push_back(ax.w[static_cast<size_t>(i) * ax.taps + first]); }
+                else if (a + 1 <= n_in - 1) { i0.push_back(a); w0.push_back(1.f); }
+                else { i0.push_back(a - 1); w0.push_back(0.f); }
+            }
+        };
+        std::vector<int32_t> wi, hi;
+        std::vector<float> ww, hw;
+        lerp(c.periph_w, c.obs_w, wi, ww);
+        if (fast_expand) lerp(c.periph_h, c.obs_h, hi, hw);
+        if (fast_expand) { o_ewi = pool.add_i(wi); o_eww = pool.add_f(ww); o_ehi = pool.add_i(hi); o_ehw = pool.add_f(hw); }
+    }
+
     pl->pool_bytes = pool.words.size() * 4;
     if (cudaMalloc(&pl->pool, pl->pool_bytes) != cudaSuccess) { delete pl; return AGYM_ERR_ALLOC; }
     const cudaError_t e = cudaMemcpy(pl->pool, pool.words.data(), pl->pool_bytes, cudaMemcpyHostToDevice);
@@ -173,6 +235,22 @@ int agym_plan_create(const agym_config *cfg, agym_plan **out_plan) {
     }
     d.pool_i = reinterpret_cast<const int32_t *>(base);
     d.S_max = s_max;
+    d.fast_ingest = fast_ingest;
+    if (fast_ingest) {
+        d.cx_pair = reinterpret_cast<const int4 *>(base + o_pair);
+        d.cy_bs = reinterpret_cast<const int2 *>(base + o_ybs);
+    }
+    d.fast_squeeze = fast_squeeze;
+    d.sqw_taps4 = sq_taps4;
+    if (fast_squeeze) {
+        d.sqw_ofs = reinterpret_cast<const int2 *>(base + o_sqofs);
+        d.sqw_w = reinterpret_cast<const float *>(base + o_sqw);
+    }
+    d.fast_expand = fast_expand;
+    if (fast_expand) {
+        d.exw_i0 = ip(o_ewi); d.exw_w0 = reinterpret_cast<const float *>(base + o_eww);
+        d.exh_i0 = ip(o_ehi); d.exh_w0 = reinterpret_cast<const float *>(base + o_ehw);
+    }
     *out_plan = pl;
     return AGYM_OK;
 }

@@ -47,9 +47,11 @@ __device__ __forceinline__ uint32_t quant_u8(float v) {
     return (uint32_t)min(max(q, 0), 255);
 }
 
-// fov_loc update of the fixed fovea, run by one thread per env (fov_env.py:187-199).
-__device__ void update_loc_fixed(const DevPlan &p, int n, const double *action, const uint8_t *ctrl, int32_t *loc,
-                                 int &r, int &c) {
+// fov_loc update of the fixed fovea (fov_env.py:187-199).  STORE: write the new loc back
+// (one thread per env); otherwise only compute it.
+template <bool STORE = true>
+__device__ __forceinline__ void update_loc_fixed(const DevPlan &p, int n, const double *action, const uint8_t *ctrl,
+                                                 int32_t *loc, int &r, int &c) {
     const int mode = ctrl ? ctrl[n] : AGYM_FOV_APPLY;
     r = loc[2 * n];
     c = loc[2 * n + 1];
@@ -65,8 +67,10 @@ __device__ void update_loc_fixed(const DevPlan &p, int n, const double *action, 
         r = clip_rint(a0, 0.0, (double)(p.S_h - p.f_h));
         c = clip_rint(a1, 0.0, (double)(p.S_w - p.f_w));
     }
-    loc[2 * n] = r;
-    loc[2 * n + 1] = c;
+    if (STORE) {
+        loc[2 * n] = r;
+        loc[2 * n + 1] = c;
+    }
 }
 
 // ------------------------------------------------------------------ separable resamples
@@ -257,6 +261,150 @@ __global__ void __launch_bounds__(kThreads) k_ingest_atari(const __grid_constant
     if (pcache) {  // uniform branch
         __syncthreads();
         squeeze_to_cache(p, s_frame, s_t1, pcache + ((size_t)n * p.K + slot) * p.p_h * p.p_w, tid, kThreads);
+    }
+}
+
+// Squeeze along W straight from a u8 frame in shared memory (fov_env.py:367, W pass): every
+// output column reads one 16-byte window, realigned with funnel shifts so that the byte ->
+// float conversions use compile-time byte selectors (I2F.U8 Rx.Bn).
+__device__ __forceinline__ void squeeze_w_fast(const DevPlan &p, const uint8_t *s_frame, float *s_t1, int tid, int nt) {
+    const int total = p.S_h * p.p_w;
+    const FastDiv fd(p.p_w);
+    const int nq = p.sqw_taps4 >> 2;
+    for (int t = tid; t < total; t += nt) {
+        const int y = fd.div(t), i = t - y * p.p_w;
+        const int2 o = __ldg(p.sqw_ofs + i);
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(s_frame + y * p.S_w + o.x);
+        const uint32_t w0 = src[0], w1 = src[1], w2 = src[2], w3 = src[3];
+        const uint32_t a[4] = {__funnelshift_r(w0, w1, o.y), __funnelshift_r(w1, w2, o.y), __funnelshift_r(w2, w3, o.y),
+                               w3 >> o.y};
+        const float4 *wt = reinterpret_cast<const float4 *>(p.sqw_w + i * p.sqw_taps4);
+        float acc = 0.f;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            if (q < nq) {
+                const float4 w = __ldg(wt + q);
+                const uint32_t v = a[q];
+                acc = fmaf(w.x, (float)(v & 0xffu), acc);
+                acc = fmaf(w.y, (float)((v >> 8) & 0xffu), acc);
+                acc = fmaf(w.z, (float)((v >> 16) & 0xffu), acc);
+                acc = fmaf(w.w, (float)(v >> 24), acc);
+            }
+        }
+        s_t1[t] = acc;
+    }
+}
+
+// Fast ingest (geometry checked at plan creation): the horizontal pass as IDP.2A on byte pairs
+// picked with PRMT from two aligned words, the vertical pass as two IMAD.HI; one thread owns
+// two adjacent output columns and walks a segment of output rows.
+template <int CH>
+__global__ void __launch_bounds__(kThreads) k_ingest_atari_fast(const __grid_constant__ DevPlan p,
+                                                                const uint8_t *__restrict__ fa,
+                                                                const uint8_t *__restrict__ fb,
+                                                                const uint8_t *__restrict__ flags,
+                                                                uint8_t *__restrict__ ring, int32_t *__restrict__ head,
+                                                                float *__restrict__ pcache) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int n = blockIdx.x, tid = threadIdx.x;
+    const int fl = flags[n];
+    if (fl & AGYM_FLAG_IDLE) return;
+    const int slot = (head[n] + 1) % p.K;
+    const int rows2 = 2 * p.S_h;
+    const size_t gray_bytes = (size_t)rows2 * p.raw_w;
+    uint8_t *s_gray = smem;
+    uint8_t *s_frame = s_gray + align16(2 * gray_bytes + 16);
+    float *s_t1 = reinterpret_cast<float *>(s_frame + align16(p.plane + 16));
+    __syncthreads();  // every thread has read head[n]
+    if (tid == 0) head[n] = slot;
+
+    const int vpr = p.raw_w / 16;
+    const FastDiv fd_vpr(vpr);
+    const size_t frame_bytes = (size_t)p.raw_h * p.raw_w * CH;
+#pragma unroll 1
+    for (int fr = 0; fr < 2; ++fr) {
+        if (!(fl & (1 << fr))) continue;
+        const uint8_t *src = (fr ? fb : fa) + frame_bytes * n;
+        uint8_t *dst = s_gray + gray_bytes * fr;
+#pragma unroll 4
+        for (int t = tid; t < rows2 * vpr; t += kThreads) {
+            const int sr = fd_vpr.div(t), g = t - sr * vpr;
+            const int srow = __ldg(((sr & 1) ? p.cy_s1 : p.cy_s0) + (sr >> 1));
+            uint4 o;
+            if (CH == 1) {
+                o = ld_stream128(src + (size_t)srow * p.raw_w + 16 * g);
+            } else {
+                const uint8_t *q = src + ((size_t)srow * p.raw_w + 16 * g) * 3;
+                uint32_t w[12];
+                *reinterpret_cast<uint4 *>(w) = ld_stream128(q);
+                *reinterpret_cast<uint4 *>(w + 4) = ld_stream128(q + 16);
+                *reinterpret_cast<uint4 *>(w + 8) = ld_stream128(q + 32);
+                uint32_t out[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const int j = 3 * i;
+                    const uint32_t c0 = (w[j >> 2] >> (8 * (j & 3))) & 0xffu;
+                    const uint32_t c1 = (w[(j + 1) >> 2] >> (8 * ((j + 1) & 3))) & 0xffu;
+                    const uint32_t c2 = (w[(j + 2) >> 2] >> (8 * ((j + 2) & 3))) & 0xffu;
+                    const uint32_t yv = (p.lw0 * c0 + p.lw1 * c1 + p.lw2 * c2 + 16384u) >> 15;
+                    out[i >> 2] |= yv << (8 * (i & 3));
+                }
+                o = make_uint4(out[0], out[1], out[2], out[3]);
+            }
+            *reinterpret_cast<uint4 *>(dst + (size_t)sr * p.raw_w + 16 * g) = o;
+        }
+    }
+    if (fl & AGYM_FLAG_HARD_RESET) {
+        const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
+        for (int k = 0; k < p.K; ++k) {
+            if (k == slot) continue;
+            uint4 *z = reinterpret_cast<uint4 *>(ring + ((size_t)n * p.K + k) * p.plane);
+            for (int i = tid; i < p.plane / 16; i += kThreads) z[i] = z4;
+            if (pcache) {
+                float *zc = pcache + ((size_t)n * p.K + k) * p.p_h * p.p_w;
+                for (int i = tid; i < p.p_h * p.p_w; i += kThreads) zc[i] = 0.f;
+            }
+        }
+    }
+    __syncthreads();
+
+    const int pairs = p.S_w >> 1, segs = kThreads / pairs;
+    const int g = tid / pairs, pi = tid - g * pairs;
+    if (g < segs) {
+        const int4 px = __ldg(p.cx_pair + pi);  // {aligned byte offset, PRMT selector, coef(x0), coef(x0+1)}
+        const int rows_per = (p.S_h + segs - 1) / segs;
+        const int y_end = min(p.S_h, (g + 1) * rows_per);
+        for (int y = g * rows_per; y < y_end; ++y) {
+            const int2 bs = __ldg(p.cy_bs + y);  // {b0 << 16, b1 << 16}
+            uint32_t m0 = 0u, m1 = 0u;
+#pragma unroll
+            for (int fr = 0; fr < 2; ++fr) {
+                if (!(fl & (1 << fr))) continue;
+                const uint8_t *r0 = s_gray + gray_bytes * fr + (size_t)(2 * y) * p.raw_w + px.x;
+                const uint32_t a0 = *reinterpret_cast<const uint32_t *>(r0);
+                const uint32_t a1 = *reinterpret_cast<const uint32_t *>(r0 + 4);
+                const uint32_t b0 = *reinterpret_cast<const uint32_t *>(r0 + p.raw_w);
+                const uint32_t b1 = *reinterpret_cast<const uint32_t *>(r0 + p.raw_w + 4);
+                const uint32_t qa = __byte_perm(a0, a1, (uint32_t)px.y), qb = __byte_perm(b0, b1, (uint32_t)px.y);
+                const uint32_t h00 = __dp2a_lo((uint32_t)px.z, qa, 0u), h01 = __dp2a_hi((uint32_t)px.w, qa, 0u);
+                const uint32_t h10 = __dp2a_lo((uint32_t)px.z, qb, 0u), h11 = __dp2a_hi((uint32_t)px.w, qb, 0u);
+                const uint32_t v0 = (__umulhi((uint32_t)bs.x, h00 >> 4) + __umulhi((uint32_t)bs.y, h10 >> 4) + 2u) >> 2;
+                const uint32_t v1 = (__umulhi((uint32_t)bs.x, h01 >> 4) + __umulhi((uint32_t)bs.y, h11 >> 4) + 2u) >> 2;
+                m0 = max(m0, v0);
+                m1 = max(m1, v1);
+            }
+            *reinterpret_cast<uint16_t *>(s_frame + y * p.S_w + 2 * pi) = (uint16_t)(min(m0, 255u) | (min(m1, 255u) << 8));
+        }
+    }
+    __syncthreads();
+    uint4 *out4 = reinterpret_cast<uint4 *>(ring + ((size_t)n * p.K + slot) * p.plane);
+    for (int i = tid; i < p.plane / 16; i += kThreads) out4[i] = reinterpret_cast<const uint4 *>(s_frame)[i];
+    if (pcache) {  // uniform
+        float *dst = pcache + ((size_t)n * p.K + slot) * p.p_h * p.p_w;
+        if (p.fast_squeeze) squeeze_w_fast(p, s_frame, s_t1, tid, kThreads);
+        else resample_w<uint8_t>(s_frame, p.S_w, s_t1, p.p_w, p.S_h, p.sq_w, tid, kThreads);
+        __syncthreads();
+        resample_h<float>(s_t1, p.p_w, dst, p.p_w, p.p_w, p.sq_h, tid, kThreads);
     }
 }
 
@@ -485,6 +633,135 @@ __global__ void __launch_bounds__(kThreads) k_observe_peripheral(const __grid_co
     }
 }
 
+// Fast peripheral observe (cached squeeze, bilinear-upsample expand): both expand passes are
+// two-tap lerps r = b + w0 * (a - b).  The cached squeeze is biased by 49152.5 on load; lerp
+// weights sum to one, so the bias rides through both passes and the rounded pixel
+// floor(v + 0.5) ends up in byte 1 of the float's bit pattern (ulp there is 2^-8, so the total
+// evaluation error is < 0.01 u8 LSB) — no float->int conversion, one PRMT tree per 4 pixels.
+constexpr float kBias = 49152.5f;
+
+template <int KG>  // frames handled together by one thread (K % KG == 0)
+__global__ void __launch_bounds__(128) k_observe_peripheral_fast(const __grid_constant__ DevPlan p,
+                                                                 const uint8_t *__restrict__ ring,
+                                                                 const int32_t *__restrict__ head,
+                                                                 const float *__restrict__ pcache,
+                                                                 const double *__restrict__ action,
+                                                                 const uint8_t *__restrict__ ctrl,
+                                                                 int32_t *__restrict__ loc, uint8_t *__restrict__ out,
+                                                                 int ysegs) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int n = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+    const int pp = p.p_h * p.p_w, K = p.K;
+    float *s_sq = reinterpret_cast<float *>(smem);                 // [K][p_h][p_w], biased
+    float *s_t2 = s_sq + ((K * pp + 3) & ~3);                      // [K][p_h][S_w]
+    int32_t *s_hi = reinterpret_cast<int32_t *>(s_t2 + K * p.p_h * p.S_w);
+    float *s_hw = reinterpret_cast<float *>(s_hi + p.S_h);
+    uint32_t *s_fov = reinterpret_cast<uint32_t *>(s_hw + p.S_h);  // [K][f_h][nw]: the ring words under the fovea
+    const int quads = p.S_w >> 2;
+    const uint32_t wpp = (uint32_t)p.plane >> 2;  // words per plane
+    // every thread derives the new fov_loc itself (broadcast loads, no barrier); thread 0 stores it
+    int r0, c0;
+    update_loc_fixed<false>(p, n, action, ctrl, loc, r0, c0);
+    const int h = head[n];
+    const int wq0 = c0 >> 2, nw = ((c0 + p.f_w - 1) >> 2) - wq0 + 1, nw_max = (p.f_w + 3) / 4 + 1;
+    {   // all global reads of this env are issued here, back to back: fovea words, cached squeeze, tables
+        const uint32_t *ring_w = reinterpret_cast<const uint32_t *>(ring) + (size_t)n * K * wpp;
+        const int per_k = p.f_h * nw;
+        const FastDiv fd_pk(per_k), fd_nw(nw);
+        for (int i = tid; i < K * per_k; i += nt) {
+            const int k = fd_pk.div(i), rem = i - k * per_k;
+            const int yy = fd_nw.div(rem), ww = rem - yy * nw;
+            s_fov[(k * p.f_h + yy) * nw_max + ww] =
+                __ldg(ring_w + (uint32_t)((h + 1 + k) % K) * wpp + (uint32_t)(r0 + yy) * quads + wq0 + ww);
+        }
+    }
+    for (int i = tid; i < p.S_h; i += nt) { s_hi[i] = __ldg(p.exh_i0 + i); s_hw[i] = __ldg(p.exh_w0 + i); }
+    for (int k = 0; k < K; ++k) {  // logical frame k <- ring slot (h+1+k)%K
+        const float4 *c4 = reinterpret_cast<const float4 *>(pcache + ((size_t)n * K + (h + 1 + k) % K) * pp);
+        float4 *d4 = reinterpret_cast<float4 *>(s_sq + k * pp);
+        for (int i = tid; i < pp / 4; i += nt) {
+            float4 v = __ldg(c4 + i);
+            v.x += kBias; v.y += kBias; v.z += kBias; v.w += kBias;
+            d4[i] = v;
+        }
+    }
+    const int g = tid / quads, q = tid - g * quads;
+    const bool active = g < ysegs;
+    int i0[4];
+    float w0x[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        i0[i] = active ? __ldg(p.exw_i0 + 4 * q + i) : 0;
+        w0x[i] = active ? __ldg(p.exw_w0 + 4 * q + i) : 0.f;
+    }
+    __syncthreads();
+    // pass 1 (along W): t2[row][x] = s[i0+1] + w0 * (s[i0] - s[i0+1]); one thread = 4 columns of a row
+    if (active) {
+        const int nrows = K * p.p_h;
+        const float *s = s_sq + g * p.p_w;
+        float *t = s_t2 + g * p.S_w + 4 * q;
+        for (int r = g; r < nrows; r += ysegs, s += ysegs * p.p_w, t += ysegs * p.S_w) {
+            float4 o;
+            { const float a = s[i0[0]], b = s[i0[0] + 1]; o.x = fmaf(w0x[0], a - b, b); }
+            { const float a = s[i0[1]], b = s[i0[1] + 1]; o.y = fmaf(w0x[1], a - b, b); }
+            { const float a = s[i0[2]], b = s[i0[2] + 1]; o.z = fmaf(w0x[2], a - b, b); }
+            { const float a = s[i0[3]], b = s[i0[3] + 1]; o.w = fmaf(w0x[3], a - b, b); }
+            *reinterpret_cast<float4 *>(t) = o;
+        }
+    }
+    __syncthreads();
+    if (tid == 0) { loc[2 * n] = r0; loc[2 * n + 1] = c0; }
+    if (!active) return;
+    // pass 2 (along H) + rounding + fovea paste: 4 pixels x KG frames per thread and row
+    const uint32_t fov_mask = word_mask(4 * q, c0, c0 + p.f_w);
+    const int rf = fov_mask ? r0 : (1 << 29);   // this column quad never meets the fovea
+    const int rows_per = (p.S_h + ysegs - 1) / ysegs;
+    const int y_begin = g * rows_per, y_end = min(p.S_h, y_begin + rows_per);
+    uint32_t *out_q = reinterpret_cast<uint32_t *>(out) + (size_t)n * K * wpp + (size_t)y_begin * quads + q;
+    for (int k0 = 0; k0 < K; k0 += KG) {
+        uint32_t oo[KG];  // word offset of logical frame k0+kk's output plane
+#pragma unroll
+        for (int kk = 0; kk < KG; ++kk) oo[kk] = (uint32_t)(k0 + kk) * wpp;
+        const uint32_t *fv = s_fov + (k0 * p.f_h - rf) * nw_max + (q - wq0);
+        uint32_t *o = out_q;  // walks down the rows of this thread's segment
+        const float *t2g = s_t2 + (size_t)k0 * p.p_h * p.S_w + 4 * q;
+        int y = y_begin;
+        while (y < y_end) {
+            const int j0 = s_hi[y];
+            float4 b[KG], d[KG];
+#pragma unroll
+            for (int kk = 0; kk < KG; ++kk) {
+                const float *r = t2g + (kk * p.p_h + j0) * p.S_w;
+                const float4 a = *reinterpret_cast<const float4 *>(r);
+                b[kk] = *reinterpret_cast<const float4 *>(r + p.S_w);
+                d[kk] = make_float4(a.x - b[kk].x, a.y - b[kk].y, a.z - b[kk].z, a.w - b[kk].w);
+            }
+            do {
+                const float w0 = s_hw[y];
+                uint32_t word[KG];
+#pragma unroll
+                for (int kk = 0; kk < KG; ++kk) {
+                    const uint32_t u0 = __float_as_uint(fmaf(w0, d[kk].x, b[kk].x));
+                    const uint32_t u1 = __float_as_uint(fmaf(w0, d[kk].y, b[kk].y));
+                    const uint32_t u2 = __float_as_uint(fmaf(w0, d[kk].z, b[kk].z));
+                    const uint32_t u3 = __float_as_uint(fmaf(w0, d[kk].w, b[kk].w));
+                    word[kk] = __byte_perm(__byte_perm(u0, u1, 0x0051), __byte_perm(u2, u3, 0x0051), 0x5410);
+                }
+                if ((unsigned)(y - rf) < (unsigned)p.f_h) {  // fovea rows: paste the sharp bytes (fov_env.py:385-386)
+                    const uint32_t *sh = fv + y * nw_max;
+#pragma unroll
+                    for (int kk = 0; kk < KG; ++kk)
+                        word[kk] = (word[kk] & ~fov_mask) | (sh[kk * p.f_h * nw_max] & fov_mask);
+                }
+#pragma unroll
+                for (int kk = 0; kk < KG; ++kk) o[oo[kk]] = word[kk];
+                o += quads;
+                ++y;
+            } while (y < y_end && s_hi[y] == j0);
+        }
+    }
+}
+
 // --------------------------------------------------------------------- observe: flexible
 // FlexibleFovealEnv._fov_step + _get_fov_state (fov_env.py:270-330).
 __device__ __forceinline__ AxisRef flex_axis(const DevPlan &p, int axis, int family, int r, int n_in) {
@@ -629,6 +906,18 @@ cudaError_t launch_ingest_atari(const DevPlan &p, const uint8_t *fa, const uint8
     size_t smem = a16(sizeof(int32_t) * 3 * (p.S_w + p.S_h)) + a16(2 * (size_t)2 * p.S_h * p.raw_w);
     if (pcache) smem += a16(p.plane) + sizeof(float) * p.S_h * p.p_w;
     cudaError_t e;
+    if (p.fast_ingest) {
+        size_t fs = a16(2 * (size_t)2 * p.S_h * p.raw_w + 16) + a16(p.plane + 16);
+        if (pcache) fs += sizeof(float) * p.S_h * p.p_w;
+        if (p.raw_c == 1) {
+            if ((e = set_smem(k_ingest_atari_fast<1>, fs)) != cudaSuccess) return e;
+            k_ingest_atari_fast<1><<<p.N, kThreads, fs, st>>>(p, fa, fb, flags, ring, head, pcache);
+        } else {
+            if ((e = set_smem(k_ingest_atari_fast<3>, fs)) != cudaSuccess) return e;
+            k_ingest_atari_fast<3><<<p.N, kThreads, fs, st>>>(p, fa, fb, flags, ring, head, pcache);
+        }
+        return cudaGetLastError();
+    }
     if (p.raw_c == 1) {
         if ((e = set_smem(k_ingest_atari<1>, smem)) != cudaSuccess) return e;
         k_ingest_atari<1><<<p.N, kThreads, smem, st>>>(p, fa, fb, flags, ring, head, pcache);
@@ -673,6 +962,22 @@ cudaError_t launch_observe_peripheral(const DevPlan &p, const uint8_t *ring, con
                                       cudaStream_t st) {
     const size_t smem = a16(p.plane) + sizeof(float) * ((size_t)p.S_h * p.p_w + (size_t)p.p_h * p.p_w + (size_t)p.p_h * p.S_w);
     cudaError_t e;
+    const int quads = p.S_w / 4;
+    if (pcache && p.fast_expand && quads <= 128 && (p.p_h * p.p_w) % 4 == 0) {
+        const int ysegs = 128 / quads;
+        const int threads = ((quads * ysegs + 31) / 32) * 32;
+        const size_t fs = sizeof(float) * (((size_t)p.K * p.p_h * p.p_w + 3) / 4 * 4 + (size_t)p.K * p.p_h * p.S_w) +
+                          8 * (size_t)p.S_h + 4 * (size_t)p.K * p.f_h * ((p.f_w + 3) / 4 + 1);
+#define AGYM_LAUNCH_PF(KG)                                                                                    \
+    if ((e = set_smem(k_observe_peripheral_fast<KG>, fs)) != cudaSuccess) return e;                           \
+    k_observe_peripheral_fast<KG><<<p.N, threads, fs, st>>>(p, ring, head, pcache, action, ctrl, loc, out, ysegs);
+        if (p.K % 4 == 0) { AGYM_LAUNCH_PF(4) }
+        else if (p.K % 3 == 0) { AGYM_LAUNCH_PF(3) }
+        else if (p.K % 2 == 0) { AGYM_LAUNCH_PF(2) }
+        else { AGYM_LAUNCH_PF(1) }
+#undef AGYM_LAUNCH_PF
+        return cudaGetLastError();
+    }
     if (pcache) {
         if ((e = set_smem(k_observe_peripheral<true>, smem)) != cudaSuccess) return e;
         k_observe_peripheral<true><<<p.N, kThreads, smem, st>>>(p, ring, head, pcache, action, ctrl, loc, out);

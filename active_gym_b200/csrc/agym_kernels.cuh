@@ -37,6 +37,20 @@ struct DevPlan {
     const FlexEntry *flex;  // [2][3][S_max+1]
     const int32_t *pool_i;  // pool base viewed as int32
     int32_t S_max;
+    // ---- fast paths (0 = geometry not eligible, use the generic kernels)
+    // ingest: per output-column pair {byte offset of the aligned word, PRMT selector, coef(x0), coef(x0+1)}
+    // and per output row {b0 << 16, b1 << 16} (atari_env.py:74 fixed-point bilinear, dp2a form)
+    int32_t fast_ingest;
+    const int4 *cx_pair;    // [S_w / 2]
+    const int2 *cy_bs;      // [S_h]
+    // squeeze along W from u8 rows: per output column {aligned byte offset, shift, first weight index}
+    int32_t fast_squeeze, sqw_taps4;  // taps padded to a multiple of 4
+    const int2 *sqw_ofs;    // [p_w] {aligned byte offset, 8 * (xmin & 3)}
+    const float *sqw_w;     // [p_w][sqw_taps4]
+    // expand p -> S as two-tap lerps: out = t[i0+1] + w0 * (t[i0] - t[i0+1])
+    int32_t fast_expand;
+    const int32_t *exw_i0, *exh_i0;   // [S_w], [S_h]
+    const float *exw_w0, *exh_w0;
 };
 
 cudaError_t launch_ingest_atari(const DevPlan &p, const uint8_t *fa, const uint8_t *fb, const uint8_t *flags,

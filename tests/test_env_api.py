@@ -142,7 +142,7 @@ def test_atari_single_env_dropin_matches_reference(name):
             ref = (want.astype(np.float32) / np.float32(255)).astype(np.float64)
             assert np.array_equal(obs, ref), (name, i)  # the reference's float64 values, bit for bit
         else:
-            assert np.abs(obs * 255.0 - want).max() <= 0.5 + 1e-3, (name, i)
+            assert np.abs(obs * 255.0 - want).max() <= 0.5 + 1e-2, (name, i)
 
 
 @pytest.mark.gpu
@@ -169,7 +169,7 @@ def test_dmc_single_env_dropin_matches_reference(name):
         if meta["exact"]:
             assert np.array_equal(obs, (want_all[i].astype(np.float32) / np.float32(255)).astype(np.float64))
         else:
-            assert np.abs(obs * 255.0 - want_all[i]).max() <= 0.5 + 1e-3
+            assert np.abs(obs * 255.0 - want_all[i]).max() <= 0.5 + 1e-2
 
 
 @pytest.mark.gpu
