@@ -12,6 +12,8 @@
 // round-off of it for the antialiased resamples.
 #include "agym_kernels.cuh"
 
+#include <algorithm>
+
 #include "../../include/agym_b200.h"
 
 namespace agym {
@@ -640,51 +642,55 @@ __global__ void __launch_bounds__(kThreads) k_observe_peripheral(const __grid_co
 // evaluation error is < 0.01 u8 LSB) — no float->int conversion, one PRMT tree per 4 pixels.
 constexpr float kBias = 49152.5f;
 
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async4(void *smem_dst, const void *gmem_src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// fov_loc update as its own (tiny) launch, so that the persistent observe kernel below can
+// prefetch the next env's fovea while it works on the current one (fov_env.py:187-199).
+__global__ void k_update_loc_fixed(const __grid_constant__ DevPlan p, const double *__restrict__ action,
+                                   const uint8_t *__restrict__ ctrl, int32_t *__restrict__ loc) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= p.N) return;
+    int r, c;
+    update_loc_fixed<true>(p, n, action, ctrl, loc, r, c);
+}
+
+// Persistent CTAs (a few per SM) walk the env batch; each env's inputs — the cached squeeze of
+// its K ring slots and the ring words under its fovea — are fetched with cp.async into a
+// double buffer one env ahead, so HBM latency is hidden behind the previous env's arithmetic.
+// One thread owns 4 adjacent columns and a segment of rows for KG frames: it builds the two
+// W-expanded source rows it needs in registers (sliding down the source rows), then emits
+// one output word per frame and row: 4 FFMA + 3 PRMT each.
 template <int KG>  // frames handled together by one thread (K % KG == 0)
 __global__ void __launch_bounds__(128) k_observe_peripheral_fast(const __grid_constant__ DevPlan p,
                                                                  const uint8_t *__restrict__ ring,
                                                                  const int32_t *__restrict__ head,
                                                                  const float *__restrict__ pcache,
-                                                                 const double *__restrict__ action,
-                                                                 const uint8_t *__restrict__ ctrl,
-                                                                 int32_t *__restrict__ loc, uint8_t *__restrict__ out,
-                                                                 int ysegs) {
+                                                                 const int32_t *__restrict__ loc,
+                                                                 uint8_t *__restrict__ out, int ysegs) {
     extern __shared__ __align__(16) uint8_t smem[];
-    const int n = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
-    const int pp = p.p_h * p.p_w, K = p.K;
-    float *s_sq = reinterpret_cast<float *>(smem);                 // [K][p_h][p_w], biased
-    float *s_t2 = s_sq + ((K * pp + 3) & ~3);                      // [K][p_h][S_w]
-    int32_t *s_hi = reinterpret_cast<int32_t *>(s_t2 + K * p.p_h * p.S_w);
-    float *s_hw = reinterpret_cast<float *>(s_hi + p.S_h);
-    uint32_t *s_fov = reinterpret_cast<uint32_t *>(s_hw + p.S_h);  // [K][f_h][nw]: the ring words under the fovea
+    const int tid = threadIdx.x;
+    constexpr int nt = 128;
+    const int pp = p.p_h * p.p_w, K = p.K, N = p.N;
     const int quads = p.S_w >> 2;
     const uint32_t wpp = (uint32_t)p.plane >> 2;  // words per plane
-    // every thread derives the new fov_loc itself (broadcast loads, no barrier); thread 0 stores it
-    int r0, c0;
-    update_loc_fixed<false>(p, n, action, ctrl, loc, r0, c0);
-    const int h = head[n];
-    const int wq0 = c0 >> 2, nw = ((c0 + p.f_w - 1) >> 2) - wq0 + 1, nw_max = (p.f_w + 3) / 4 + 1;
-    {   // all global reads of this env are issued here, back to back: fovea words, cached squeeze, tables
-        const uint32_t *ring_w = reinterpret_cast<const uint32_t *>(ring) + (size_t)n * K * wpp;
-        const int per_k = p.f_h * nw;
-        const FastDiv fd_pk(per_k), fd_nw(nw);
-        for (int i = tid; i < K * per_k; i += nt) {
-            const int k = fd_pk.div(i), rem = i - k * per_k;
-            const int yy = fd_nw.div(rem), ww = rem - yy * nw;
-            s_fov[(k * p.f_h + yy) * nw_max + ww] =
-                __ldg(ring_w + (uint32_t)((h + 1 + k) % K) * wpp + (uint32_t)(r0 + yy) * quads + wq0 + ww);
-        }
-    }
-    for (int i = tid; i < p.S_h; i += nt) { s_hi[i] = __ldg(p.exh_i0 + i); s_hw[i] = __ldg(p.exh_w0 + i); }
-    for (int k = 0; k < K; ++k) {  // logical frame k <- ring slot (h+1+k)%K
-        const float4 *c4 = reinterpret_cast<const float4 *>(pcache + ((size_t)n * K + (h + 1 + k) % K) * pp);
-        float4 *d4 = reinterpret_cast<float4 *>(s_sq + k * pp);
-        for (int i = tid; i < pp / 4; i += nt) {
-            float4 v = __ldg(c4 + i);
-            v.x += kBias; v.y += kBias; v.z += kBias; v.w += kBias;
-            d4[i] = v;
-        }
-    }
+    const int nw_max = (p.f_w + 3) / 4 + 1;
+    const int sq_words = (K * pp + 3) & ~3, buf_words = sq_words + ((K * p.f_h * nw_max + 3) & ~3);
+    float *bufs = reinterpret_cast<float *>(smem);  // [2]{ sq [K][p_h][p_w] | fov [K][f_h][nw_max] }
+    int32_t *s_hi = reinterpret_cast<int32_t *>(bufs + 2 * buf_words);
+    float *s_hw = reinterpret_cast<float *>(s_hi + p.S_h);
+    const uint32_t *ring_w = reinterpret_cast<const uint32_t *>(ring);
+    uint32_t *out_w = reinterpret_cast<uint32_t *>(out);
+    const int2 *loc2 = reinterpret_cast<const int2 *>(loc);
+
+    // ---- per-thread constants
     const int g = tid / quads, q = tid - g * quads;
     const bool active = g < ysegs;
     int i0[4];
@@ -694,71 +700,110 @@ __global__ void __launch_bounds__(128) k_observe_peripheral_fast(const __grid_co
         i0[i] = active ? __ldg(p.exw_i0 + 4 * q + i) : 0;
         w0x[i] = active ? __ldg(p.exw_w0 + 4 * q + i) : 0.f;
     }
-    __syncthreads();
-    // pass 1 (along W): t2[row][x] = s[i0+1] + w0 * (s[i0] - s[i0+1]); one thread = 4 columns of a row
-    if (active) {
-        const int nrows = K * p.p_h;
-        const float *s = s_sq + g * p.p_w;
-        float *t = s_t2 + g * p.S_w + 4 * q;
-        for (int r = g; r < nrows; r += ysegs, s += ysegs * p.p_w, t += ysegs * p.S_w) {
-            float4 o;
-            { const float a = s[i0[0]], b = s[i0[0] + 1]; o.x = fmaf(w0x[0], a - b, b); }
-            { const float a = s[i0[1]], b = s[i0[1] + 1]; o.y = fmaf(w0x[1], a - b, b); }
-            { const float a = s[i0[2]], b = s[i0[2] + 1]; o.z = fmaf(w0x[2], a - b, b); }
-            { const float a = s[i0[3]], b = s[i0[3] + 1]; o.w = fmaf(w0x[3], a - b, b); }
-            *reinterpret_cast<float4 *>(t) = o;
-        }
-    }
-    __syncthreads();
-    if (tid == 0) { loc[2 * n] = r0; loc[2 * n + 1] = c0; }
-    if (!active) return;
-    // pass 2 (along H) + rounding + fovea paste: 4 pixels x KG frames per thread and row
-    const uint32_t fov_mask = word_mask(4 * q, c0, c0 + p.f_w);
-    const int rf = fov_mask ? r0 : (1 << 29);   // this column quad never meets the fovea
     const int rows_per = (p.S_h + ysegs - 1) / ysegs;
-    const int y_begin = g * rows_per, y_end = min(p.S_h, y_begin + rows_per);
-    uint32_t *out_q = reinterpret_cast<uint32_t *>(out) + (size_t)n * K * wpp + (size_t)y_begin * quads + q;
-    for (int k0 = 0; k0 < K; k0 += KG) {
-        uint32_t oo[KG];  // word offset of logical frame k0+kk's output plane
-#pragma unroll
-        for (int kk = 0; kk < KG; ++kk) oo[kk] = (uint32_t)(k0 + kk) * wpp;
-        const uint32_t *fv = s_fov + (k0 * p.f_h - rf) * nw_max + (q - wq0);
-        uint32_t *o = out_q;  // walks down the rows of this thread's segment
-        const float *t2g = s_t2 + (size_t)k0 * p.p_h * p.S_w + 4 * q;
-        int y = y_begin;
-        while (y < y_end) {
-            const int j0 = s_hi[y];
-            float4 b[KG], d[KG];
-#pragma unroll
-            for (int kk = 0; kk < KG; ++kk) {
-                const float *r = t2g + (kk * p.p_h + j0) * p.S_w;
-                const float4 a = *reinterpret_cast<const float4 *>(r);
-                b[kk] = *reinterpret_cast<const float4 *>(r + p.S_w);
-                d[kk] = make_float4(a.x - b[kk].x, a.y - b[kk].y, a.z - b[kk].z, a.w - b[kk].w);
+    const int y_begin = g * rows_per, y_end = active ? min(p.S_h, y_begin + rows_per) : y_begin;
+    const int frow_k = tid / p.f_h, frow_y = tid - frow_k * p.f_h;  // this thread's fovea row (k, yy) when tid < K*f_h
+    const int pp4 = pp >> 2;
+    for (int i = tid; i < p.S_h; i += nt) { s_hi[i] = __ldg(p.exh_i0 + i); s_hw[i] = __ldg(p.exh_w0 + i); }
+
+    auto issue = [&](int env, int2 lc, int hh, int b) {
+        float *sq = bufs + b * buf_words;
+        uint32_t *fv = reinterpret_cast<uint32_t *>(sq + sq_words);
+        const size_t slot0 = (size_t)env * K;
+        for (int c = tid; c < pp4; c += nt)  // cached squeeze: logical frame k <- ring slot (hh+1+k)%K
+            for (int k = 0; k < K; ++k) {
+                int slot = hh + 1 + k;
+                slot -= slot >= K ? K : 0;
+                cp_async16(sq + k * pp + 4 * c, pcache + (slot0 + slot) * pp + 4 * c);
             }
-            do {
-                const float w0 = s_hw[y];
-                uint32_t word[KG];
-#pragma unroll
-                for (int kk = 0; kk < KG; ++kk) {
-                    const uint32_t u0 = __float_as_uint(fmaf(w0, d[kk].x, b[kk].x));
-                    const uint32_t u1 = __float_as_uint(fmaf(w0, d[kk].y, b[kk].y));
-                    const uint32_t u2 = __float_as_uint(fmaf(w0, d[kk].z, b[kk].z));
-                    const uint32_t u3 = __float_as_uint(fmaf(w0, d[kk].w, b[kk].w));
-                    word[kk] = __byte_perm(__byte_perm(u0, u1, 0x0051), __byte_perm(u2, u3, 0x0051), 0x5410);
-                }
-                if ((unsigned)(y - rf) < (unsigned)p.f_h) {  // fovea rows: paste the sharp bytes (fov_env.py:385-386)
-                    const uint32_t *sh = fv + y * nw_max;
-#pragma unroll
-                    for (int kk = 0; kk < KG; ++kk)
-                        word[kk] = (word[kk] & ~fov_mask) | (sh[kk * p.f_h * nw_max] & fov_mask);
-                }
-#pragma unroll
-                for (int kk = 0; kk < KG; ++kk) o[oo[kk]] = word[kk];
-                o += quads;
-                ++y;
-            } while (y < y_end && s_hi[y] == j0);
+        const int wq0 = lc.y >> 2, nw = ((lc.y + p.f_w - 1) >> 2) - wq0 + 1;
+        for (int r = tid, k = frow_k, yy = frow_y; r < K * p.f_h; r += nt, k = r / p.f_h, yy = r - k * p.f_h) {
+            int slot = hh + 1 + k;
+            slot -= slot >= K ? K : 0;
+            const uint32_t *src = ring_w + (slot0 + slot) * wpp + (uint32_t)(lc.x + yy) * quads + wq0;
+            uint32_t *dst = fv + (k * p.f_h + yy) * nw_max;
+            for (int w = 0; w < nw; ++w) cp_async4(dst + w, src + w);
         }
+    };
+
+    int e = blockIdx.x;
+    int2 lc = make_int2(0, 0), lc1 = lc;
+    int hh = 0, hh1 = 0;
+    if (e < N) { lc = loc2[e]; hh = head[e]; issue(e, lc, hh, 0); }
+    cp_async_commit();
+    if (e + (int)gridDim.x < N) { lc1 = loc2[e + gridDim.x]; hh1 = head[e + gridDim.x]; }
+
+    for (int it = 0; e < N; e += gridDim.x, ++it) {
+        const int en = e + gridDim.x;
+        if (en < N) issue(en, lc1, hh1, (it + 1) & 1);
+        cp_async_commit();
+        int2 lc2 = lc1;
+        int hh2 = hh1;
+        if (en + (int)gridDim.x < N) { lc2 = loc2[en + gridDim.x]; hh2 = head[en + gridDim.x]; }
+        cp_async_wait<1>();
+        __syncthreads();
+
+        if (active) {
+            const float *sq = bufs + (it & 1) * buf_words;
+            const uint32_t *fvb = reinterpret_cast<const uint32_t *>(sq + sq_words);
+            const int r0 = lc.x, c0 = lc.y;
+            const uint32_t fov_mask = word_mask(4 * q, c0, c0 + p.f_w);
+            const int rf = fov_mask ? r0 : (1 << 29);  // this column quad never meets the fovea
+            for (int k0 = 0; k0 < K; k0 += KG) {
+                uint32_t oo[KG];
+#pragma unroll
+                for (int kk = 0; kk < KG; ++kk) oo[kk] = (uint32_t)(k0 + kk) * wpp;
+                uint32_t *o = out_w + (size_t)e * K * wpp + (size_t)y_begin * quads + q;
+                const uint32_t *fv = fvb + (k0 * p.f_h - rf) * nw_max + (q - (c0 >> 2));
+                const float *sqk = sq + k0 * pp;
+                // W-expanded source row j of frame k0+kk at this thread's 4 columns (biased)
+                auto build_row = [&](int j, int kk) {
+                    const float *s = sqk + kk * pp + j * p.p_w;
+                    float4 t;
+                    { const float u = s[i0[0]], v = s[i0[0] + 1]; t.x = fmaf(w0x[0], u - v, v + kBias); }
+                    { const float u = s[i0[1]], v = s[i0[1] + 1]; t.y = fmaf(w0x[1], u - v, v + kBias); }
+                    { const float u = s[i0[2]], v = s[i0[2] + 1]; t.z = fmaf(w0x[2], u - v, v + kBias); }
+                    { const float u = s[i0[3]], v = s[i0[3] + 1]; t.w = fmaf(w0x[3], u - v, v + kBias); }
+                    return t;
+                };
+                int y = y_begin, j_have = -2;
+                float4 b[KG], d[KG];
+                while (y < y_end) {
+                    const int j0 = s_hi[y];
+#pragma unroll
+                    for (int kk = 0; kk < KG; ++kk) {
+                        const float4 a = (j0 == j_have + 1) ? b[kk] : build_row(j0, kk);
+                        b[kk] = build_row(j0 + 1, kk);
+                        d[kk] = make_float4(a.x - b[kk].x, a.y - b[kk].y, a.z - b[kk].z, a.w - b[kk].w);
+                    }
+                    j_have = j0;
+                    do {
+                        const float w0 = s_hw[y];
+                        uint32_t word[KG];
+#pragma unroll
+                        for (int kk = 0; kk < KG; ++kk) {
+                            const uint32_t u0 = __float_as_uint(fmaf(w0, d[kk].x, b[kk].x));
+                            const uint32_t u1 = __float_as_uint(fmaf(w0, d[kk].y, b[kk].y));
+                            const uint32_t u2 = __float_as_uint(fmaf(w0, d[kk].z, b[kk].z));
+                            const uint32_t u3 = __float_as_uint(fmaf(w0, d[kk].w, b[kk].w));
+                            word[kk] = __byte_perm(__byte_perm(u0, u1, 0x0051), __byte_perm(u2, u3, 0x0051), 0x5410);
+                        }
+                        if ((unsigned)(y - rf) < (unsigned)p.f_h) {  // fovea rows: paste the sharp bytes (fov_env.py:385-386)
+                            const uint32_t *sh = fv + y * nw_max;
+#pragma unroll
+                            for (int kk = 0; kk < KG; ++kk)
+                                word[kk] = (word[kk] & ~fov_mask) | (sh[kk * p.f_h * nw_max] & fov_mask);
+                        }
+#pragma unroll
+                        for (int kk = 0; kk < KG; ++kk) o[oo[kk]] = word[kk];
+                        o += quads;
+                        ++y;
+                    } while (y < y_end && s_hi[y] == j0);
+                }
+            }
+        }
+        __syncthreads();  // the buffer just read is the target of the prefetch issued next
+        lc = lc1; hh = hh1; lc1 = lc2; hh1 = hh2;
     }
 }
 
@@ -965,12 +1010,17 @@ cudaError_t launch_observe_peripheral(const DevPlan &p, const uint8_t *ring, con
     const int quads = p.S_w / 4;
     if (pcache && p.fast_expand && quads <= 128 && (p.p_h * p.p_w) % 4 == 0) {
         const int ysegs = 128 / quads;
-        const int threads = ((quads * ysegs + 31) / 32) * 32;
-        const size_t fs = sizeof(float) * (((size_t)p.K * p.p_h * p.p_w + 3) / 4 * 4 + (size_t)p.K * p.p_h * p.S_w) +
-                          8 * (size_t)p.S_h + 4 * (size_t)p.K * p.f_h * ((p.f_w + 3) / 4 + 1);
+        const int nw_max = (p.f_w + 3) / 4 + 1;
+        const size_t buf_words = (((size_t)p.K * p.p_h * p.p_w + 3) & ~size_t(3)) + (((size_t)p.K * p.f_h * nw_max + 3) & ~size_t(3));
+        const size_t fs = 4 * (2 * buf_words + 2 * (size_t)p.S_h);
+        k_update_loc_fixed<<<(p.N + 255) / 256, 256, 0, st>>>(p, action, ctrl, loc);
+        int dev = 0, sms = 148, occ = 1;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
 #define AGYM_LAUNCH_PF(KG)                                                                                    \
     if ((e = set_smem(k_observe_peripheral_fast<KG>, fs)) != cudaSuccess) return e;                           \
-    k_observe_peripheral_fast<KG><<<p.N, threads, fs, st>>>(p, ring, head, pcache, action, ctrl, loc, out, ysegs);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_observe_peripheral_fast<KG>, 128, fs);              \
+    k_observe_peripheral_fast<KG><<<std::min(p.N, sms * std::max(occ, 1)), 128, fs, st>>>(p, ring, head, pcache, loc, out, ysegs);
         if (p.K % 4 == 0) { AGYM_LAUNCH_PF(4) }
         else if (p.K % 3 == 0) { AGYM_LAUNCH_PF(3) }
         else if (p.K % 2 == 0) { AGYM_LAUNCH_PF(2) }
