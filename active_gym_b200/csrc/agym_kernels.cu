@@ -13,6 +13,7 @@
 #include "agym_kernels.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "../../include/agym_b200.h"
 
@@ -410,6 +411,161 @@ __global__ void __launch_bounds__(kThreads) k_ingest_atari_fast(const __grid_con
     }
 }
 
+// ---- TMA (cp.async.bulk) + mbarrier helpers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    }
+}
+// 1-D bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// Persistent, TMA-fed ingest for gray frames: every CTA walks the env batch in "units" of
+// S_h/halves output rows.  The source rows a unit samples (only those: rows the resize never
+// reads stay in HBM) are brought in by cp.async.bulk row-pair copies into a two-deep ring of
+// shared-memory buffers, one unit ahead of the arithmetic, completion tracked by mbarriers —
+// so the HBM stream never waits for the fixed-point math and vice versa.
+__global__ void __launch_bounds__(kThreads) k_ingest_atari_tma(const __grid_constant__ DevPlan p,
+                                                               const uint8_t *__restrict__ fa,
+                                                               const uint8_t *__restrict__ fb,
+                                                               const uint8_t *__restrict__ flags,
+                                                               uint8_t *__restrict__ ring, int32_t *__restrict__ head,
+                                                               float *__restrict__ pcache, int halves) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    __shared__ __align__(8) uint64_t bars[2];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int N = p.N, K = p.K, raw_w = p.raw_w;
+    const int R = p.S_h / halves;                         // output rows per unit
+    const uint32_t pair_stride = 2 * raw_w + 16;           // +16: spreads the row pairs over the banks
+    const uint32_t frame_unit = R * pair_stride;           // one frame's staged rows of a unit
+    const uint32_t buf_bytes = (uint32_t)align16(2 * frame_unit + 16);
+    uint8_t *bufs = smem;
+    uint8_t *s_frame = bufs + 2 * buf_bytes;
+    float *s_t1 = reinterpret_cast<float *>(s_frame + align16(p.plane + 16));
+    const size_t frame_bytes = (size_t)p.raw_h * raw_w;
+
+    if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_fence_init(); }
+    __syncthreads();
+
+    // unit `it` of this CTA: env = blockIdx.x + (it / halves) * gridDim.x, half = it % halves
+    const int my_envs = (N - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int my_units = my_envs * halves;
+    auto issue = [&](int it) {  // warp 0 only
+        const int n = blockIdx.x + (it / halves) * gridDim.x, hf = it % halves, b = it & 1;
+        const int fl = flags[n];
+        const int nvalid = (fl & AGYM_FLAG_IDLE) ? 0 : __popc(fl & 3);
+        if (lane == 0) mbar_expect_tx(&bars[b], (uint32_t)nvalid * R * 2 * raw_w);
+        __syncwarp();
+        if (nvalid == 0) return;
+        for (int fr = 0; fr < 2; ++fr) {
+            if (!(fl & (1 << fr))) continue;
+            const uint8_t *src = (fr ? fb : fa) + frame_bytes * n;
+            uint8_t *dst = bufs + b * buf_bytes + fr * frame_unit;
+            for (int yy = lane; yy < R; yy += 32) {
+                const int y = hf * R + yy;
+                const int s0 = __ldg(p.cy_s0 + y), s1 = __ldg(p.cy_s1 + y);
+                uint8_t *d = dst + yy * pair_stride;
+                if (s1 == s0 + 1) {
+                    bulk_g2s(d, src + (size_t)s0 * raw_w, 2 * raw_w, &bars[b]);
+                } else {
+                    bulk_g2s(d, src + (size_t)s0 * raw_w, raw_w, &bars[b]);
+                    bulk_g2s(d + raw_w, src + (size_t)s1 * raw_w, raw_w, &bars[b]);
+                }
+            }
+        }
+    };
+
+    // per-thread constants of the resize: two adjacent output columns, a segment of rows
+    const int pairs = p.S_w >> 1, segs = kThreads / pairs;
+    const int g = tid / pairs, pi = tid - g * pairs;
+    const bool worker = g < segs;
+    const int4 px = worker ? __ldg(p.cx_pair + pi) : make_int4(0, 0, 0, 0);
+    const int rows_per = (R + segs - 1) / segs;
+    const int yy_begin = g * rows_per, yy_end = worker ? min(R, yy_begin + rows_per) : yy_begin;
+
+    if (warp == 0 && my_units > 0) issue(0);
+    int slot = 0;
+    for (int it = 0; it < my_units; ++it) {
+        const int n = blockIdx.x + (it / halves) * gridDim.x, hf = it % halves, b = it & 1;
+        if (warp == 0 && it + 1 < my_units) issue(it + 1);  // buffer (it+1)&1 was released by the barrier below
+        const int fl = flags[n];
+        const bool idle = fl & AGYM_FLAG_IDLE;
+        if (hf == 0) slot = (head[n] + 1) % K;
+        mbar_wait(&bars[b], (it >> 1) & 1);
+        if (!idle) {
+            const uint8_t *buf = bufs + b * buf_bytes + px.x;
+            for (int yy = yy_begin; yy < yy_end; ++yy) {
+                const int y = hf * R + yy;
+                const int2 bs = __ldg(p.cy_bs + y);  // {b0 << 16, b1 << 16}
+                uint32_t m0 = 0u, m1 = 0u;
+#pragma unroll
+                for (int fr = 0; fr < 2; ++fr) {
+                    if (!(fl & (1 << fr))) continue;
+                    const uint8_t *r0 = buf + fr * frame_unit + yy * pair_stride;
+                    const uint32_t a0 = *reinterpret_cast<const uint32_t *>(r0);
+                    const uint32_t a1 = *reinterpret_cast<const uint32_t *>(r0 + 4);
+                    const uint32_t b0 = *reinterpret_cast<const uint32_t *>(r0 + raw_w);
+                    const uint32_t b1 = *reinterpret_cast<const uint32_t *>(r0 + raw_w + 4);
+                    const uint32_t qa = __byte_perm(a0, a1, (uint32_t)px.y), qb = __byte_perm(b0, b1, (uint32_t)px.y);
+                    const uint32_t h00 = __dp2a_lo((uint32_t)px.z, qa, 0u), h01 = __dp2a_hi((uint32_t)px.w, qa, 0u);
+                    const uint32_t h10 = __dp2a_lo((uint32_t)px.z, qb, 0u), h11 = __dp2a_hi((uint32_t)px.w, qb, 0u);
+                    const uint32_t v0 = (__umulhi((uint32_t)bs.x, h00 >> 4) + __umulhi((uint32_t)bs.y, h10 >> 4) + 2u) >> 2;
+                    const uint32_t v1 = (__umulhi((uint32_t)bs.x, h01 >> 4) + __umulhi((uint32_t)bs.y, h11 >> 4) + 2u) >> 2;
+                    m0 = max(m0, v0);
+                    m1 = max(m1, v1);
+                }
+                *reinterpret_cast<uint16_t *>(s_frame + y * p.S_w + 2 * pi) = (uint16_t)(min(m0, 255u) | (min(m1, 255u) << 8));
+            }
+        }
+        __syncthreads();  // unit consumed: its buffer may be refilled; this half of s_frame is complete
+        if (hf == halves - 1 && !idle) {
+            if (tid == 0) head[n] = slot;
+            if (fl & AGYM_FLAG_HARD_RESET) {
+                const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
+                for (int k = 0; k < K; ++k) {
+                    if (k == slot) continue;
+                    uint4 *z = reinterpret_cast<uint4 *>(ring + ((size_t)n * K + k) * p.plane);
+                    for (int i = tid; i < p.plane / 16; i += kThreads) z[i] = z4;
+                    if (pcache) {
+                        float *zc = pcache + ((size_t)n * K + k) * p.p_h * p.p_w;
+                        for (int i = tid; i < p.p_h * p.p_w; i += kThreads) zc[i] = 0.f;
+                    }
+                }
+            }
+            uint4 *out4 = reinterpret_cast<uint4 *>(ring + ((size_t)n * K + slot) * p.plane);
+            for (int i = tid; i < p.plane / 16; i += kThreads) out4[i] = reinterpret_cast<const uint4 *>(s_frame)[i];
+            if (pcache) {
+                float *dst = pcache + ((size_t)n * K + slot) * p.p_h * p.p_w;
+                if (p.fast_squeeze) squeeze_w_fast(p, s_frame, s_t1, tid, kThreads);
+                else resample_w<uint8_t>(s_frame, p.S_w, s_t1, p.p_w, p.S_h, p.sq_w, tid, kThreads);
+                __syncthreads();
+                resample_h<float>(s_t1, p.p_w, dst, p.p_w, p.p_w, p.sq_h, tid, kThreads);
+            }
+            __syncthreads();  // s_frame / s_t1 are reused by the next env
+        }
+    }
+}
+
 // -------------------------------------------------------------------------- ingest: DMC
 // DMCEnv._get_obs pixel/grey branch + stack logic (dmc_env.py:175-183, 193-195, 206-207,
 // 228-230): 15-bit luma of the frame rendered at obs_size, pushed as is (no max-pool).
@@ -676,16 +832,15 @@ __global__ void __launch_bounds__(128) k_observe_peripheral_fast(const __grid_co
                                                                  const int32_t *__restrict__ loc,
                                                                  uint8_t *__restrict__ out, int ysegs) {
     extern __shared__ __align__(16) uint8_t smem[];
-    const int tid = threadIdx.x;
-    constexpr int nt = 128;
-    const int pp = p.p_h * p.p_w, K = p.K, N = p.N;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int pp = p.p_h * p.p_w, K = p.K, N = p.N, f_h = p.f_h;
     const int quads = p.S_w >> 2;
     const uint32_t wpp = (uint32_t)p.plane >> 2;  // words per plane
     const int nw_max = (p.f_w + 3) / 4 + 1;
-    const int sq_words = (K * pp + 3) & ~3, buf_words = sq_words + ((K * p.f_h * nw_max + 3) & ~3);
+    const int sq_words = (K * pp + 3) & ~3, buf_words = sq_words + ((K * f_h * nw_max + 3) & ~3);
     float *bufs = reinterpret_cast<float *>(smem);  // [2]{ sq [K][p_h][p_w] | fov [K][f_h][nw_max] }
     int32_t *s_hi = reinterpret_cast<int32_t *>(bufs + 2 * buf_words);
-    float *s_hw = reinterpret_cast<float *>(s_hi + p.S_h);
+    float *s_hw = reinterpret_cast<float *>(s_hi + p.S_h + 1);
     const uint32_t *ring_w = reinterpret_cast<const uint32_t *>(ring);
     uint32_t *out_w = reinterpret_cast<uint32_t *>(out);
     const int2 *loc2 = reinterpret_cast<const int2 *>(loc);
@@ -693,35 +848,36 @@ __global__ void __launch_bounds__(128) k_observe_peripheral_fast(const __grid_co
     // ---- per-thread constants
     const int g = tid / quads, q = tid - g * quads;
     const bool active = g < ysegs;
-    int i0[4];
+    int ofs[4];  // float offsets of the left tap of this thread's 4 columns inside a squeezed row
     float w0x[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        i0[i] = active ? __ldg(p.exw_i0 + 4 * q + i) : 0;
+        ofs[i] = active ? __ldg(p.exw_i0 + 4 * q + i) : 0;
         w0x[i] = active ? __ldg(p.exw_w0 + 4 * q + i) : 0.f;
     }
     const int rows_per = (p.S_h + ysegs - 1) / ysegs;
     const int y_begin = g * rows_per, y_end = active ? min(p.S_h, y_begin + rows_per) : y_begin;
-    const int frow_k = tid / p.f_h, frow_y = tid - frow_k * p.f_h;  // this thread's fovea row (k, yy) when tid < K*f_h
-    const int pp4 = pp >> 2;
+    const int pp4 = pp >> 2, frows = K * f_h;
     for (int i = tid; i < p.S_h; i += nt) { s_hi[i] = __ldg(p.exh_i0 + i); s_hw[i] = __ldg(p.exh_w0 + i); }
+    if (tid == 0) s_hi[p.S_h] = -1;  // sentinel: ends the last run of rows
 
     auto issue = [&](int env, int2 lc, int hh, int b) {
         float *sq = bufs + b * buf_words;
         uint32_t *fv = reinterpret_cast<uint32_t *>(sq + sq_words);
         const size_t slot0 = (size_t)env * K;
-        for (int c = tid; c < pp4; c += nt)  // cached squeeze: logical frame k <- ring slot (hh+1+k)%K
-            for (int k = 0; k < K; ++k) {
-                int slot = hh + 1 + k;
-                slot -= slot >= K ? K : 0;
-                cp_async16(sq + k * pp + 4 * c, pcache + (slot0 + slot) * pp + 4 * c);
-            }
+        for (int k = 0; k < K; ++k) {  // cached squeeze: logical frame k <- ring slot (hh+1+k)%K
+            int slot = hh + 1 + k;
+            slot -= slot >= K ? K : 0;
+            const float *src = pcache + (slot0 + slot) * pp;
+            for (int c = tid; c < pp4; c += nt) cp_async16(sq + k * pp + 4 * c, src + 4 * c);
+        }
         const int wq0 = lc.y >> 2, nw = ((lc.y + p.f_w - 1) >> 2) - wq0 + 1;
-        for (int r = tid, k = frow_k, yy = frow_y; r < K * p.f_h; r += nt, k = r / p.f_h, yy = r - k * p.f_h) {
+        for (int r = tid; r < frows; r += nt) {  // one fovea row (k, yy) per thread and pass
+            const int k = r / f_h, yy = r - k * f_h;
             int slot = hh + 1 + k;
             slot -= slot >= K ? K : 0;
             const uint32_t *src = ring_w + (slot0 + slot) * wpp + (uint32_t)(lc.x + yy) * quads + wq0;
-            uint32_t *dst = fv + (k * p.f_h + yy) * nw_max;
+            uint32_t *dst = fv + r * nw_max;
             for (int w = 0; w < nw; ++w) cp_async4(dst + w, src + w);
         }
     };
@@ -749,27 +905,31 @@ __global__ void __launch_bounds__(128) k_observe_peripheral_fast(const __grid_co
             const int r0 = lc.x, c0 = lc.y;
             const uint32_t fov_mask = word_mask(4 * q, c0, c0 + p.f_w);
             const int rf = fov_mask ? r0 : (1 << 29);  // this column quad never meets the fovea
+            const int fstride = f_h * nw_max;          // words between two frames' fovea tiles
+            uint32_t *const obase = out_w + (size_t)e * K * wpp;
             for (int k0 = 0; k0 < K; k0 += KG) {
-                uint32_t oo[KG];
+                uint32_t *ob[KG];  // loop-invariant plane bases; rows are addressed with one 32-bit index
 #pragma unroll
-                for (int kk = 0; kk < KG; ++kk) oo[kk] = (uint32_t)(k0 + kk) * wpp;
-                uint32_t *o = out_w + (size_t)e * K * wpp + (size_t)y_begin * quads + q;
-                const uint32_t *fv = fvb + (k0 * p.f_h - rf) * nw_max + (q - (c0 >> 2));
+                for (int kk = 0; kk < KG; ++kk) ob[kk] = obase + (size_t)(k0 + kk) * wpp;
+                const uint32_t *fv = fvb + (k0 * f_h - rf) * nw_max + (q - (c0 >> 2));
                 const float *sqk = sq + k0 * pp;
                 // W-expanded source row j of frame k0+kk at this thread's 4 columns (biased)
                 auto build_row = [&](int j, int kk) {
                     const float *s = sqk + kk * pp + j * p.p_w;
                     float4 t;
-                    { const float u = s[i0[0]], v = s[i0[0] + 1]; t.x = fmaf(w0x[0], u - v, v + kBias); }
-                    { const float u = s[i0[1]], v = s[i0[1] + 1]; t.y = fmaf(w0x[1], u - v, v + kBias); }
-                    { const float u = s[i0[2]], v = s[i0[2] + 1]; t.z = fmaf(w0x[2], u - v, v + kBias); }
-                    { const float u = s[i0[3]], v = s[i0[3] + 1]; t.w = fmaf(w0x[3], u - v, v + kBias); }
+                    { const float u = s[ofs[0]], v = s[ofs[0] + 1]; t.x = fmaf(w0x[0], u - v, v + kBias); }
+                    { const float u = s[ofs[1]], v = s[ofs[1] + 1]; t.y = fmaf(w0x[1], u - v, v + kBias); }
+                    { const float u = s[ofs[2]], v = s[ofs[2] + 1]; t.z = fmaf(w0x[2], u - v, v + kBias); }
+                    { const float u = s[ofs[3]], v = s[ofs[3] + 1]; t.w = fmaf(w0x[3], u - v, v + kBias); }
                     return t;
                 };
                 int y = y_begin, j_have = -2;
+                uint32_t idx = (uint32_t)y_begin * quads + q;
+                const int32_t *hp = s_hi + y_begin;
+                const float *wp = s_hw + y_begin;
+                int j0 = *hp;
                 float4 b[KG], d[KG];
                 while (y < y_end) {
-                    const int j0 = s_hi[y];
 #pragma unroll
                     for (int kk = 0; kk < KG; ++kk) {
                         const float4 a = (j0 == j_have + 1) ? b[kk] : build_row(j0, kk);
@@ -777,8 +937,10 @@ __global__ void __launch_bounds__(128) k_observe_peripheral_fast(const __grid_co
                         d[kk] = make_float4(a.x - b[kk].x, a.y - b[kk].y, a.z - b[kk].z, a.w - b[kk].w);
                     }
                     j_have = j0;
+                    int jn;
                     do {
-                        const float w0 = s_hw[y];
+                        const float w0 = *wp++;
+                        jn = *++hp;  // source row of the next output row (sentinel past the end)
                         uint32_t word[KG];
 #pragma unroll
                         for (int kk = 0; kk < KG; ++kk) {
@@ -788,17 +950,17 @@ __global__ void __launch_bounds__(128) k_observe_peripheral_fast(const __grid_co
                             const uint32_t u3 = __float_as_uint(fmaf(w0, d[kk].w, b[kk].w));
                             word[kk] = __byte_perm(__byte_perm(u0, u1, 0x0051), __byte_perm(u2, u3, 0x0051), 0x5410);
                         }
-                        if ((unsigned)(y - rf) < (unsigned)p.f_h) {  // fovea rows: paste the sharp bytes (fov_env.py:385-386)
+                        if ((unsigned)(y - rf) < (unsigned)f_h) {  // fovea rows: paste the sharp bytes (fov_env.py:385-386)
                             const uint32_t *sh = fv + y * nw_max;
 #pragma unroll
-                            for (int kk = 0; kk < KG; ++kk)
-                                word[kk] = (word[kk] & ~fov_mask) | (sh[kk * p.f_h * nw_max] & fov_mask);
+                            for (int kk = 0; kk < KG; ++kk) word[kk] = (word[kk] & ~fov_mask) | (sh[kk * fstride] & fov_mask);
                         }
 #pragma unroll
-                        for (int kk = 0; kk < KG; ++kk) o[oo[kk]] = word[kk];
-                        o += quads;
+                        for (int kk = 0; kk < KG; ++kk) ob[kk][idx] = word[kk];
+                        idx += quads;
                         ++y;
-                    } while (y < y_end && s_hi[y] == j0);
+                    } while (jn == j0 && y < y_end);
+                    j0 = jn;
                 }
             }
         }
@@ -943,6 +1105,9 @@ cudaError_t set_smem(F func, size_t bytes) {
 
 size_t a16(size_t v) { return (v + 15) & ~size_t(15); }
 
+// AGYM_NO_TMA=1 forces the non-persistent ingest kernel (A/B comparisons, debugging)
+const bool g_disable_tma = getenv("AGYM_NO_TMA") != nullptr;
+
 }  // namespace
 
 // --------------------------------------------------------------------------- launchers
@@ -951,6 +1116,19 @@ cudaError_t launch_ingest_atari(const DevPlan &p, const uint8_t *fa, const uint8
     size_t smem = a16(sizeof(int32_t) * 3 * (p.S_w + p.S_h)) + a16(2 * (size_t)2 * p.S_h * p.raw_w);
     if (pcache) smem += a16(p.plane) + sizeof(float) * p.S_h * p.p_w;
     cudaError_t e;
+    if (p.fast_ingest && p.raw_c == 1 && !g_disable_tma) {
+        const int halves = (p.S_h % 2 == 0) ? 2 : 1;
+        const size_t frame_unit = (size_t)(p.S_h / halves) * (2 * p.raw_w + 16);
+        size_t fs = 2 * a16(2 * frame_unit + 16) + a16(p.plane + 16);
+        if (pcache) fs += sizeof(float) * p.S_h * p.p_w;
+        if ((e = set_smem(k_ingest_atari_tma, fs)) != cudaSuccess) return e;
+        int dev = 0, sms = 148, occ = 1;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_ingest_atari_tma, kThreads, fs);
+        k_ingest_atari_tma<<<std::min(p.N, sms * std::max(occ, 1)), kThreads, fs, st>>>(p, fa, fb, flags, ring, head, pcache, halves);
+        return cudaGetLastError();
+    }
     if (p.fast_ingest) {
         size_t fs = a16(2 * (size_t)2 * p.S_h * p.raw_w + 16) + a16(p.plane + 16);
         if (pcache) fs += sizeof(float) * p.S_h * p.p_w;
@@ -1009,18 +1187,27 @@ cudaError_t launch_observe_peripheral(const DevPlan &p, const uint8_t *ring, con
     cudaError_t e;
     const int quads = p.S_w / 4;
     if (pcache && p.fast_expand && quads <= 128 && (p.p_h * p.p_w) % 4 == 0) {
-        const int ysegs = 128 / quads;
+        // rows per thread segment: a multiple of the expand pattern's period when S_h allows it
+        // (84 -> 20 repeats every 21 rows), so the lanes of a warp switch source rows together
+        int ysegs = std::max(1, 128 / quads);
+        {
+            int g = p.S_h, b2 = p.p_h;
+            while (b2) { const int t = g % b2; g = b2; b2 = t; }   // gcd(S_h, p_h)
+            const int period = p.S_h / g;
+            while (ysegs > 1 && (p.S_h % ysegs != 0 || (p.S_h / ysegs) % period != 0)) --ysegs;
+        }
+        const int threads = ((quads * ysegs + 31) / 32) * 32;
         const int nw_max = (p.f_w + 3) / 4 + 1;
         const size_t buf_words = (((size_t)p.K * p.p_h * p.p_w + 3) & ~size_t(3)) + (((size_t)p.K * p.f_h * nw_max + 3) & ~size_t(3));
-        const size_t fs = 4 * (2 * buf_words + 2 * (size_t)p.S_h);
+        const size_t fs = 4 * (2 * buf_words + 2 * (size_t)p.S_h + 2);
         k_update_loc_fixed<<<(p.N + 255) / 256, 256, 0, st>>>(p, action, ctrl, loc);
         int dev = 0, sms = 148, occ = 1;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
 #define AGYM_LAUNCH_PF(KG)                                                                                    \
     if ((e = set_smem(k_observe_peripheral_fast<KG>, fs)) != cudaSuccess) return e;                           \
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_observe_peripheral_fast<KG>, 128, fs);              \
-    k_observe_peripheral_fast<KG><<<std::min(p.N, sms * std::max(occ, 1)), 128, fs, st>>>(p, ring, head, pcache, loc, out, ysegs);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_observe_peripheral_fast<KG>, threads, fs);              \
+    k_observe_peripheral_fast<KG><<<std::min(p.N, sms * std::max(occ, 1)), threads, fs, st>>>(p, ring, head, pcache, loc, out, ysegs);
         if (p.K % 4 == 0) { AGYM_LAUNCH_PF(4) }
         else if (p.K % 3 == 0) { AGYM_LAUNCH_PF(3) }
         else if (p.K % 2 == 0) { AGYM_LAUNCH_PF(2) }
