@@ -440,41 +440,59 @@ __device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gmem_src, u
                  : "memory");
 }
 
-// Persistent, TMA-fed ingest for gray frames: every CTA walks the env batch in "units" of
-// S_h/halves output rows.  The source rows a unit samples (only those: rows the resize never
-// reads stay in HBM) are brought in by cp.async.bulk row-pair copies into a two-deep ring of
-// shared-memory buffers, one unit ahead of the arithmetic, completion tracked by mbarriers —
-// so the HBM stream never waits for the fixed-point math and vice versa.
-__global__ void __launch_bounds__(kThreads) k_ingest_atari_tma(const __grid_constant__ DevPlan p,
-                                                               const uint8_t *__restrict__ fa,
-                                                               const uint8_t *__restrict__ fb,
-                                                               const uint8_t *__restrict__ flags,
-                                                               uint8_t *__restrict__ ring, int32_t *__restrict__ head,
-                                                               float *__restrict__ pcache, int halves) {
+// Persistent, TMA-fed ingest for gray frames: every CTA walks the env batch in "units" of R
+// output rows.  The source rows a unit samples (only those: rows the resize never reads stay
+// in HBM) are brought in by cp.async.bulk row-pair copies into a two-deep ring of shared-memory
+// buffers, one unit ahead of the arithmetic, completion tracked by mbarriers — so the HBM
+// stream never waits for the fixed-point math and vice versa.  Warp 8 is the producer (it only
+// issues copies); warps 0-7 resize.  RAW_W / S_W / R_T > 0 bake the strides of the standard
+// geometry (210x160 -> 84x84) into the instruction immediates; 0 = take them from the plan.
+constexpr int kIngestThreads = kThreads + 32;
+
+template <int RAW_W, int S_W, int R_T>
+__global__ void __launch_bounds__(kIngestThreads, 3) k_ingest_atari_tma(const __grid_constant__ DevPlan p,
+                                                                     const uint8_t *__restrict__ fa,
+                                                                     const uint8_t *__restrict__ fb,
+                                                                     const uint8_t *__restrict__ flags,
+                                                                     uint8_t *__restrict__ ring,
+                                                                     int32_t *__restrict__ head,
+                                                                     float *__restrict__ pcache, int units) {
     extern __shared__ __align__(16) uint8_t smem[];
     __shared__ __align__(8) uint64_t bars[2];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int N = p.N, K = p.K, raw_w = p.raw_w;
-    const int R = p.S_h / halves;                         // output rows per unit
-    const uint32_t pair_stride = 2 * raw_w + 16;           // +16: spreads the row pairs over the banks
-    const uint32_t frame_unit = R * pair_stride;           // one frame's staged rows of a unit
-    const uint32_t buf_bytes = (uint32_t)align16(2 * frame_unit + 16);
+    const int N = p.N, K = p.K;
+    const int raw_w = RAW_W ? RAW_W : p.raw_w;
+    const int S_w = S_W ? S_W : p.S_w;
+    const int R = R_T ? R_T : p.S_h / units;             // output rows per unit
+    const int pair_stride = 2 * raw_w + 16;               // +16: spreads the row pairs over the banks
+    const int frame_unit = R * pair_stride;               // one frame's staged rows of a unit
+    const int buf_bytes = (2 * frame_unit + 16 + 15) & ~15;
     uint8_t *bufs = smem;
     uint8_t *s_frame = bufs + 2 * buf_bytes;
     float *s_t1 = reinterpret_cast<float *>(s_frame + align16(p.plane + 16));
+    int2 *s_ybs = reinterpret_cast<int2 *>(s_t1 + (pcache ? p.S_h * p.p_w : 0));   // [S_h] {b0<<16, b1<<16}
+    int2 *s_rows = s_ybs + p.S_h;                                                    // [S_h] {s0, s1}
+    float *s_sqw = reinterpret_cast<float *>(s_rows + p.S_h);                        // [p_w][taps4] squeeze weights
     const size_t frame_bytes = (size_t)p.raw_h * raw_w;
 
     if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_fence_init(); }
+    for (int y = tid; y < p.S_h; y += kIngestThreads) {
+        s_ybs[y] = __ldg(p.cy_bs + y);
+        s_rows[y] = make_int2(__ldg(p.cy_s0 + y), __ldg(p.cy_s1 + y));
+    }
+    if (pcache && p.fast_squeeze)
+        for (int i = tid; i < p.p_w * p.sqw_taps4; i += kIngestThreads) s_sqw[i] = __ldg(p.sqw_w + i);
     __syncthreads();
 
-    // unit `it` of this CTA: env = blockIdx.x + (it / halves) * gridDim.x, half = it % halves
+    // unit `it` of this CTA: env = blockIdx.x + (it / units) * gridDim.x, part = it % units
     const int my_envs = (N - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-    const int my_units = my_envs * halves;
-    auto issue = [&](int it) {  // warp 0 only
-        const int n = blockIdx.x + (it / halves) * gridDim.x, hf = it % halves, b = it & 1;
+    const int my_units = my_envs * units;
+    const bool producer = warp == kThreads / 32;
+    auto issue = [&](int it) {  // producer warp only
+        const int n = blockIdx.x + (it / units) * gridDim.x, part = it % units, b = it & 1;
         const int fl = flags[n];
         const int nvalid = (fl & AGYM_FLAG_IDLE) ? 0 : __popc(fl & 3);
-        if (lane == 0) mbar_expect_tx(&bars[b], (uint32_t)nvalid * R * 2 * raw_w);
+        if (lane == 0) mbar_expect_tx(&bars[b], (uint32_t)(nvalid * R * 2 * raw_w));
         __syncwarp();
         if (nvalid == 0) return;
         for (int fr = 0; fr < 2; ++fr) {
@@ -482,84 +500,138 @@ __global__ void __launch_bounds__(kThreads) k_ingest_atari_tma(const __grid_cons
             const uint8_t *src = (fr ? fb : fa) + frame_bytes * n;
             uint8_t *dst = bufs + b * buf_bytes + fr * frame_unit;
             for (int yy = lane; yy < R; yy += 32) {
-                const int y = hf * R + yy;
-                const int s0 = __ldg(p.cy_s0 + y), s1 = __ldg(p.cy_s1 + y);
+                const int2 rows = s_rows[part * R + yy];
                 uint8_t *d = dst + yy * pair_stride;
-                if (s1 == s0 + 1) {
-                    bulk_g2s(d, src + (size_t)s0 * raw_w, 2 * raw_w, &bars[b]);
+                if (rows.y == rows.x + 1) {
+                    bulk_g2s(d, src + (size_t)rows.x * raw_w, 2 * raw_w, &bars[b]);
                 } else {
-                    bulk_g2s(d, src + (size_t)s0 * raw_w, raw_w, &bars[b]);
-                    bulk_g2s(d + raw_w, src + (size_t)s1 * raw_w, raw_w, &bars[b]);
+                    bulk_g2s(d, src + (size_t)rows.x * raw_w, raw_w, &bars[b]);
+                    bulk_g2s(d + raw_w, src + (size_t)rows.y * raw_w, raw_w, &bars[b]);
                 }
             }
         }
     };
 
-    // per-thread constants of the resize: two adjacent output columns, a segment of rows
-    const int pairs = p.S_w >> 1, segs = kThreads / pairs;
+    // consumer constants: two adjacent output columns, a segment of the unit's rows
+    const int pairs = S_w >> 1, segs = kThreads / pairs;
     const int g = tid / pairs, pi = tid - g * pairs;
-    const bool worker = g < segs;
+    const bool worker = !producer && g < segs;
     const int4 px = worker ? __ldg(p.cx_pair + pi) : make_int4(0, 0, 0, 0);
     const int rows_per = (R + segs - 1) / segs;
     const int yy_begin = g * rows_per, yy_end = worker ? min(R, yy_begin + rows_per) : yy_begin;
+    // squeeze along W: one thread = one output column i (weights in registers), rows in passes
+    const int sq_rows = p.fast_squeeze ? kThreads / p.p_w : 0;
+    const int sq_i = sq_rows ? tid % p.p_w : 0, sq_y0 = sq_rows ? tid / p.p_w : 0;
+    const bool sq_worker = pcache && sq_rows && !producer && sq_y0 < sq_rows;
+    const int nq = p.sqw_taps4 >> 2;
+    const int2 sq_o = sq_worker ? __ldg(p.sqw_ofs + sq_i) : make_int2(0, 0);
+    const float4 *sqw4 = reinterpret_cast<const float4 *>(s_sqw + sq_i * p.sqw_taps4);
 
-    if (warp == 0 && my_units > 0) issue(0);
+    if (producer && my_units > 0) issue(0);
     int slot = 0;
     for (int it = 0; it < my_units; ++it) {
-        const int n = blockIdx.x + (it / halves) * gridDim.x, hf = it % halves, b = it & 1;
-        if (warp == 0 && it + 1 < my_units) issue(it + 1);  // buffer (it+1)&1 was released by the barrier below
+        const int n = blockIdx.x + (it / units) * gridDim.x, part = it % units, b = it & 1;
+        if (producer && it + 1 < my_units) issue(it + 1);  // buffer (it+1)&1 was released by the barrier below
         const int fl = flags[n];
         const bool idle = fl & AGYM_FLAG_IDLE;
-        if (hf == 0) slot = (head[n] + 1) % K;
-        mbar_wait(&bars[b], (it >> 1) & 1);
-        if (!idle) {
-            const uint8_t *buf = bufs + b * buf_bytes + px.x;
-            for (int yy = yy_begin; yy < yy_end; ++yy) {
-                const int y = hf * R + yy;
-                const int2 bs = __ldg(p.cy_bs + y);  // {b0 << 16, b1 << 16}
-                uint32_t m0 = 0u, m1 = 0u;
+        if (part == 0) slot = (head[n] + 1) % K;
+        if (worker && !idle) {
+            mbar_wait(&bars[b], (it >> 1) & 1);
+            const uint8_t *r = bufs + b * buf_bytes + px.x + yy_begin * pair_stride;
+            const int2 *ybs = s_ybs + part * R + yy_begin;
+            uint8_t *o = s_frame + (part * R + yy_begin) * S_w + 2 * pi;
+            if ((fl & 3) == 3) {  // both frames (the steady state)
+#pragma unroll 2
+                for (int yy = yy_begin; yy < yy_end; ++yy, r += pair_stride, ++ybs, o += S_w) {
+                    const int2 bs = *ybs;
+                    uint32_t m[2] = {0u, 0u};
 #pragma unroll
-                for (int fr = 0; fr < 2; ++fr) {
-                    if (!(fl & (1 << fr))) continue;
-                    const uint8_t *r0 = buf + fr * frame_unit + yy * pair_stride;
-                    const uint32_t a0 = *reinterpret_cast<const uint32_t *>(r0);
-                    const uint32_t a1 = *reinterpret_cast<const uint32_t *>(r0 + 4);
-                    const uint32_t b0 = *reinterpret_cast<const uint32_t *>(r0 + raw_w);
-                    const uint32_t b1 = *reinterpret_cast<const uint32_t *>(r0 + raw_w + 4);
-                    const uint32_t qa = __byte_perm(a0, a1, (uint32_t)px.y), qb = __byte_perm(b0, b1, (uint32_t)px.y);
-                    const uint32_t h00 = __dp2a_lo((uint32_t)px.z, qa, 0u), h01 = __dp2a_hi((uint32_t)px.w, qa, 0u);
-                    const uint32_t h10 = __dp2a_lo((uint32_t)px.z, qb, 0u), h11 = __dp2a_hi((uint32_t)px.w, qb, 0u);
-                    const uint32_t v0 = (__umulhi((uint32_t)bs.x, h00 >> 4) + __umulhi((uint32_t)bs.y, h10 >> 4) + 2u) >> 2;
-                    const uint32_t v1 = (__umulhi((uint32_t)bs.x, h01 >> 4) + __umulhi((uint32_t)bs.y, h11 >> 4) + 2u) >> 2;
-                    m0 = max(m0, v0);
-                    m1 = max(m1, v1);
+                    for (int fr = 0; fr < 2; ++fr) {
+                        const uint8_t *r0 = r + fr * frame_unit;
+                        const uint32_t a0 = *reinterpret_cast<const uint32_t *>(r0);
+                        const uint32_t a1 = *reinterpret_cast<const uint32_t *>(r0 + 4);
+                        const uint32_t b0 = *reinterpret_cast<const uint32_t *>(r0 + raw_w);
+                        const uint32_t b1 = *reinterpret_cast<const uint32_t *>(r0 + raw_w + 4);
+                        const uint32_t qa = __byte_perm(a0, a1, (uint32_t)px.y), qb = __byte_perm(b0, b1, (uint32_t)px.y);
+                        const uint32_t h00 = __dp2a_lo((uint32_t)px.z, qa, 0u), h01 = __dp2a_hi((uint32_t)px.w, qa, 0u);
+                        const uint32_t h10 = __dp2a_lo((uint32_t)px.z, qb, 0u), h11 = __dp2a_hi((uint32_t)px.w, qb, 0u);
+                        const uint32_t v0 = (__umulhi((uint32_t)bs.x, h00 >> 4) + __umulhi((uint32_t)bs.y, h10 >> 4) + 2u) >> 2;
+                        const uint32_t v1 = (__umulhi((uint32_t)bs.x, h01 >> 4) + __umulhi((uint32_t)bs.y, h11 >> 4) + 2u) >> 2;
+                        m[0] = max(m[0], v0);
+                        m[1] = max(m[1], v1);
+                    }
+                    *reinterpret_cast<uint16_t *>(o) = (uint16_t)(min(m[0], 255u) | (min(m[1], 255u) << 8));
                 }
-                *reinterpret_cast<uint16_t *>(s_frame + y * p.S_w + 2 * pi) = (uint16_t)(min(m0, 255u) | (min(m1, 255u) << 8));
+            } else {  // resets / early game-over: one frame or none
+                for (int yy = yy_begin; yy < yy_end; ++yy, r += pair_stride, ++ybs, o += S_w) {
+                    const int2 bs = *ybs;
+                    uint32_t m0 = 0u, m1 = 0u;
+                    for (int fr = 0; fr < 2; ++fr) {
+                        if (!(fl & (1 << fr))) continue;
+                        const uint8_t *r0 = r + fr * frame_unit;
+                        const uint32_t a0 = *reinterpret_cast<const uint32_t *>(r0);
+                        const uint32_t a1 = *reinterpret_cast<const uint32_t *>(r0 + 4);
+                        const uint32_t b0 = *reinterpret_cast<const uint32_t *>(r0 + raw_w);
+                        const uint32_t b1 = *reinterpret_cast<const uint32_t *>(r0 + raw_w + 4);
+                        const uint32_t qa = __byte_perm(a0, a1, (uint32_t)px.y), qb = __byte_perm(b0, b1, (uint32_t)px.y);
+                        const uint32_t h00 = __dp2a_lo((uint32_t)px.z, qa, 0u), h01 = __dp2a_hi((uint32_t)px.w, qa, 0u);
+                        const uint32_t h10 = __dp2a_lo((uint32_t)px.z, qb, 0u), h11 = __dp2a_hi((uint32_t)px.w, qb, 0u);
+                        m0 = max(m0, (__umulhi((uint32_t)bs.x, h00 >> 4) + __umulhi((uint32_t)bs.y, h10 >> 4) + 2u) >> 2);
+                        m1 = max(m1, (__umulhi((uint32_t)bs.x, h01 >> 4) + __umulhi((uint32_t)bs.y, h11 >> 4) + 2u) >> 2);
+                    }
+                    *reinterpret_cast<uint16_t *>(o) = (uint16_t)(min(m0, 255u) | (min(m1, 255u) << 8));
+                }
             }
         }
-        __syncthreads();  // unit consumed: its buffer may be refilled; this half of s_frame is complete
-        if (hf == halves - 1 && !idle) {
+        __syncthreads();  // unit consumed: its buffer may be refilled; this part of s_frame is complete
+        if (part == units - 1 && !idle) {
             if (tid == 0) head[n] = slot;
-            if (fl & AGYM_FLAG_HARD_RESET) {
-                const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
-                for (int k = 0; k < K; ++k) {
-                    if (k == slot) continue;
-                    uint4 *z = reinterpret_cast<uint4 *>(ring + ((size_t)n * K + k) * p.plane);
-                    for (int i = tid; i < p.plane / 16; i += kThreads) z[i] = z4;
-                    if (pcache) {
-                        float *zc = pcache + ((size_t)n * K + k) * p.p_h * p.p_w;
-                        for (int i = tid; i < p.p_h * p.p_w; i += kThreads) zc[i] = 0.f;
+            if (!producer) {
+                if (fl & AGYM_FLAG_HARD_RESET) {
+                    const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
+                    for (int k = 0; k < K; ++k) {
+                        if (k == slot) continue;
+                        uint4 *z = reinterpret_cast<uint4 *>(ring + ((size_t)n * K + k) * p.plane);
+                        for (int i = tid; i < p.plane / 16; i += kThreads) z[i] = z4;
+                        if (pcache) {
+                            float *zc = pcache + ((size_t)n * K + k) * p.p_h * p.p_w;
+                            for (int i = tid; i < p.p_h * p.p_w; i += kThreads) zc[i] = 0.f;
+                        }
                     }
                 }
+                uint4 *out4 = reinterpret_cast<uint4 *>(ring + ((size_t)n * K + slot) * p.plane);
+                for (int i = tid; i < p.plane / 16; i += kThreads) out4[i] = reinterpret_cast<const uint4 *>(s_frame)[i];
             }
-            uint4 *out4 = reinterpret_cast<uint4 *>(ring + ((size_t)n * K + slot) * p.plane);
-            for (int i = tid; i < p.plane / 16; i += kThreads) out4[i] = reinterpret_cast<const uint4 *>(s_frame)[i];
-            if (pcache) {
-                float *dst = pcache + ((size_t)n * K + slot) * p.p_h * p.p_w;
-                if (p.fast_squeeze) squeeze_w_fast(p, s_frame, s_t1, tid, kThreads);
-                else resample_w<uint8_t>(s_frame, p.S_w, s_t1, p.p_w, p.S_h, p.sq_w, tid, kThreads);
+            if (pcache) {  // uniform
+                if (sq_rows) {
+                    if (sq_worker) {
+                        for (int y = sq_y0; y < p.S_h; y += sq_rows) {
+                            const uint32_t *src = reinterpret_cast<const uint32_t *>(s_frame + y * S_w + sq_o.x);
+                            const uint32_t w0 = src[0], w1 = src[1], w2 = src[2], w3 = src[3];
+                            const uint32_t a[4] = {__funnelshift_r(w0, w1, sq_o.y), __funnelshift_r(w1, w2, sq_o.y),
+                                                   __funnelshift_r(w2, w3, sq_o.y), w3 >> sq_o.y};
+                            float acc = 0.f;
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                if (q < nq) {
+                                    const uint32_t v = a[q];
+                                    const float4 w = sqw4[q];
+                                    acc = fmaf(w.x, (float)(v & 0xffu), acc);
+                                    acc = fmaf(w.y, (float)((v >> 8) & 0xffu), acc);
+                                    acc = fmaf(w.z, (float)((v >> 16) & 0xffu), acc);
+                                    acc = fmaf(w.w, (float)(v >> 24), acc);
+                                }
+                            }
+                            s_t1[y * p.p_w + sq_i] = acc;
+                        }
+                    }
+                } else if (!producer) {
+                    resample_w<uint8_t>(s_frame, S_w, s_t1, p.p_w, p.S_h, p.sq_w, tid, kThreads);
+                }
                 __syncthreads();
-                resample_h<float>(s_t1, p.p_w, dst, p.p_w, p.p_w, p.sq_h, tid, kThreads);
+                if (!producer)
+                    resample_h<float>(s_t1, p.p_w, pcache + ((size_t)n * K + slot) * p.p_h * p.p_w, p.p_w, p.p_w, p.sq_h, tid,
+                                      kThreads);
             }
             __syncthreads();  // s_frame / s_t1 are reused by the next env
         }
@@ -1107,6 +1179,8 @@ size_t a16(size_t v) { return (v + 15) & ~size_t(15); }
 
 // AGYM_NO_TMA=1 forces the non-persistent ingest kernel (A/B comparisons, debugging)
 const bool g_disable_tma = getenv("AGYM_NO_TMA") != nullptr;
+// AGYM_INGEST_UNITS=n: units (shared-memory stages) per env of the TMA ingest kernel (tuning)
+const int g_units = getenv("AGYM_INGEST_UNITS") ? atoi(getenv("AGYM_INGEST_UNITS")) : 0;
 
 }  // namespace
 
@@ -1117,16 +1191,28 @@ cudaError_t launch_ingest_atari(const DevPlan &p, const uint8_t *fa, const uint8
     if (pcache) smem += a16(p.plane) + sizeof(float) * p.S_h * p.p_w;
     cudaError_t e;
     if (p.fast_ingest && p.raw_c == 1 && !g_disable_tma) {
-        const int halves = (p.S_h % 2 == 0) ? 2 : 1;
-        const size_t frame_unit = (size_t)(p.S_h / halves) * (2 * p.raw_w + 16);
-        size_t fs = 2 * a16(2 * frame_unit + 16) + a16(p.plane + 16);
-        if (pcache) fs += sizeof(float) * p.S_h * p.p_w;
-        if ((e = set_smem(k_ingest_atari_tma, fs)) != cudaSuccess) return e;
+        int units = g_units ? g_units : 3;
+        while (units > 1 && p.S_h % units != 0) --units;
+        const int R = p.S_h / units;
+        const size_t frame_unit = (size_t)R * (2 * p.raw_w + 16);
+        size_t fs = 2 * a16(2 * frame_unit + 16) + a16(p.plane + 16) + 16 * (size_t)p.S_h;
+        if (pcache) fs += sizeof(float) * ((size_t)p.S_h * p.p_w + (size_t)p.p_w * 16);
         int dev = 0, sms = 148, occ = 1;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_ingest_atari_tma, kThreads, fs);
-        k_ingest_atari_tma<<<std::min(p.N, sms * std::max(occ, 1)), kThreads, fs, st>>>(p, fa, fb, flags, ring, head, pcache, halves);
+#define AGYM_LAUNCH_TMA(...)                                                                                        \
+    {                                                                                                               \
+        if ((e = set_smem(k_ingest_atari_tma<__VA_ARGS__>, fs)) != cudaSuccess) return e;                           \
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_ingest_atari_tma<__VA_ARGS__>, kIngestThreads, fs);   \
+        k_ingest_atari_tma<__VA_ARGS__><<<std::min(p.N, sms * std::max(occ, 1)), kIngestThreads, fs, st>>>(         \
+            p, fa, fb, flags, ring, head, pcache, units);                                                           \
+    }
+        const bool std_geom = p.raw_w == 160 && p.S_w == 84;
+        if (std_geom && R == 42) AGYM_LAUNCH_TMA(160, 84, 42)
+        else if (std_geom && R == 28) AGYM_LAUNCH_TMA(160, 84, 28)
+        else if (std_geom && R == 21) AGYM_LAUNCH_TMA(160, 84, 21)
+        else AGYM_LAUNCH_TMA(0, 0, 0)
+#undef AGYM_LAUNCH_TMA
         return cudaGetLastError();
     }
     if (p.fast_ingest) {
