@@ -1,5 +1,6 @@
 // extern "C" surface of libagym_b200 (see include/agym_b200.h): plan management, argument
 // validation and dispatch to the kernels.  No torch, no C++ types cross this boundary.
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <new>
@@ -236,6 +237,20 @@ int agym_plan_create(const agym_config *cfg, agym_plan **out_plan) {
     d.pool_i = reinterpret_cast<const int32_t *>(base);
     d.S_max = s_max;
     d.fast_ingest = fast_ingest;
+    for (int u = 1; u <= 4; ++u) {  // row span of the largest unit when the output rows are cut into u units
+        d.tma_span_rows[u - 1] = 0;
+        if (c.obs_h % u != 0) continue;
+        const int R = c.obs_h / u;
+        int span = 0;
+        bool monotone = true;
+        for (int k = 0; k < u; ++k) {
+            const int lo = cy.s0[k * R], hi = cy.s1[k * R + R - 1];
+            for (int y = k * R; y < k * R + R; ++y) monotone = monotone && cy.s0[y] >= lo && cy.s1[y] <= hi;
+            span = std::max(span, hi - lo + 1);
+        }
+        // a stage holds both frames' spans; keep two stages well inside one SM's shared memory
+        if (monotone && 2 * (2 * (static_cast<size_t>(span) * c.raw_w + 16)) <= 96 * 1024) d.tma_span_rows[u - 1] = span;
+    }
     if (fast_ingest) {
         d.cx_pair = reinterpret_cast<const int4 *>(base + o_pair);
         d.cy_bs = reinterpret_cast<const int2 *>(base + o_ybs);

@@ -440,45 +440,60 @@ __device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gmem_src, u
                  : "memory");
 }
 
-// Persistent, TMA-fed ingest for gray frames: every CTA walks the env batch in "units" of R
-// output rows.  The source rows a unit samples (only those: rows the resize never reads stay
-// in HBM) are brought in by cp.async.bulk row-pair copies into a two-deep ring of shared-memory
-// buffers, one unit ahead of the arithmetic, completion tracked by mbarriers — so the HBM
-// stream never waits for the fixed-point math and vice versa.  Warp 8 is the producer (it only
-// issues copies); warps 0-7 resize.  RAW_W / S_W / R_T > 0 bake the strides of the standard
-// geometry (210x160 -> 84x84) into the instruction immediates; 0 = take them from the plan.
-constexpr int kIngestThreads = kThreads + 32;
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// barrier among the consumer warps only (the producer warp never joins it)
+__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kThreads) : "memory"); }
 
-template <int RAW_W, int S_W, int R_T>
+// Persistent, TMA-fed ingest for gray frames.  Every CTA walks the env batch in "units" of R
+// output rows; for each unit ONE cp.async.bulk per frame brings the contiguous span of source
+// rows the unit samples into a ring of shared-memory stages, tracked by full/empty mbarriers
+// (the canonical TMA producer/consumer pipeline): warp 8 is the producer, warps 0-7 resize.
+// HBM streaming and the fixed-point arithmetic therefore overlap inside every CTA.
+// RAW_W / S_W > 0 bake the strides of the standard geometry (210x160 -> 84x84) into the
+// instruction immediates; 0 = take them from the plan.
+constexpr int kIngestThreads = kThreads + 32;
+constexpr int kStages = 2;
+
+template <int RAW_W, int S_W>
 __global__ void __launch_bounds__(kIngestThreads, 3) k_ingest_atari_tma(const __grid_constant__ DevPlan p,
-                                                                     const uint8_t *__restrict__ fa,
-                                                                     const uint8_t *__restrict__ fb,
-                                                                     const uint8_t *__restrict__ flags,
-                                                                     uint8_t *__restrict__ ring,
-                                                                     int32_t *__restrict__ head,
-                                                                     float *__restrict__ pcache, int units) {
+                                                                        const uint8_t *__restrict__ fa,
+                                                                        const uint8_t *__restrict__ fb,
+                                                                        const uint8_t *__restrict__ flags,
+                                                                        uint8_t *__restrict__ ring,
+                                                                        int32_t *__restrict__ head,
+                                                                        float *__restrict__ pcache, int units,
+                                                                        int span_rows) {
     extern __shared__ __align__(16) uint8_t smem[];
-    __shared__ __align__(8) uint64_t bars[2];
+    __shared__ __align__(8) uint64_t full[kStages], empty[kStages];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int N = p.N, K = p.K;
     const int raw_w = RAW_W ? RAW_W : p.raw_w;
     const int S_w = S_W ? S_W : p.S_w;
-    const int R = R_T ? R_T : p.S_h / units;             // output rows per unit
-    const int pair_stride = 2 * raw_w + 16;               // +16: spreads the row pairs over the banks
-    const int frame_unit = R * pair_stride;               // one frame's staged rows of a unit
-    const int buf_bytes = (2 * frame_unit + 16 + 15) & ~15;
-    uint8_t *bufs = smem;
-    uint8_t *s_frame = bufs + 2 * buf_bytes;
+    const int R = p.S_h / units;                          // output rows per unit
+    const int frame_stride = span_rows * raw_w + 16;      // one frame's staged row span of a unit (+ pad)
+    const int stage_bytes = (2 * frame_stride + 15) & ~15;
+    uint8_t *stages = smem;
+    uint8_t *s_frame = stages + kStages * stage_bytes;
     float *s_t1 = reinterpret_cast<float *>(s_frame + align16(p.plane + 16));
-    int2 *s_ybs = reinterpret_cast<int2 *>(s_t1 + (pcache ? p.S_h * p.p_w : 0));   // [S_h] {b0<<16, b1<<16}
-    int2 *s_rows = s_ybs + p.S_h;                                                    // [S_h] {s0, s1}
-    float *s_sqw = reinterpret_cast<float *>(s_rows + p.S_h);                        // [p_w][taps4] squeeze weights
+    int4 *s_row = reinterpret_cast<int4 *>(s_t1 + (pcache ? p.S_h * p.p_w : 0));  // [S_h] {ofs0, ofs1, b0<<16, b1<<16}
+    int2 *s_span = reinterpret_cast<int2 *>(s_row + p.S_h);                       // [units] {first row, bytes}
+    float *s_sqw = reinterpret_cast<float *>(s_span + ((units + 1) & ~1));        // [p_w][taps4], 16-byte aligned
     const size_t frame_bytes = (size_t)p.raw_h * raw_w;
 
-    if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_fence_init(); }
+    if (tid == 0) {
+        for (int i = 0; i < kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], kThreads / 32); }
+        mbar_fence_init();
+    }
     for (int y = tid; y < p.S_h; y += kIngestThreads) {
-        s_ybs[y] = __ldg(p.cy_bs + y);
-        s_rows[y] = make_int2(__ldg(p.cy_s0 + y), __ldg(p.cy_s1 + y));
+        const int lo = __ldg(p.cy_s0 + (y / R) * R);     // first source row of this row's unit
+        const int2 bs = __ldg(p.cy_bs + y);
+        s_row[y] = make_int4((__ldg(p.cy_s0 + y) - lo) * raw_w, (__ldg(p.cy_s1 + y) - lo) * raw_w, bs.x, bs.y);
+    }
+    for (int u = tid; u < units; u += kIngestThreads) {
+        const int lo = __ldg(p.cy_s0 + u * R), hi = __ldg(p.cy_s1 + u * R + R - 1);
+        s_span[u] = make_int2(lo, (hi - lo + 1) * raw_w);
     }
     if (pcache && p.fast_squeeze)
         for (int i = tid; i < p.p_w * p.sqw_taps4; i += kIngestThreads) s_sqw[i] = __ldg(p.sqw_w + i);
@@ -487,154 +502,145 @@ __global__ void __launch_bounds__(kIngestThreads, 3) k_ingest_atari_tma(const __
     // unit `it` of this CTA: env = blockIdx.x + (it / units) * gridDim.x, part = it % units
     const int my_envs = (N - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     const int my_units = my_envs * units;
-    const bool producer = warp == kThreads / 32;
-    auto issue = [&](int it) {  // producer warp only
-        const int n = blockIdx.x + (it / units) * gridDim.x, part = it % units, b = it & 1;
-        const int fl = flags[n];
-        const int nvalid = (fl & AGYM_FLAG_IDLE) ? 0 : __popc(fl & 3);
-        if (lane == 0) mbar_expect_tx(&bars[b], (uint32_t)(nvalid * R * 2 * raw_w));
-        __syncwarp();
-        if (nvalid == 0) return;
-        for (int fr = 0; fr < 2; ++fr) {
-            if (!(fl & (1 << fr))) continue;
-            const uint8_t *src = (fr ? fb : fa) + frame_bytes * n;
-            uint8_t *dst = bufs + b * buf_bytes + fr * frame_unit;
-            for (int yy = lane; yy < R; yy += 32) {
-                const int2 rows = s_rows[part * R + yy];
-                uint8_t *d = dst + yy * pair_stride;
-                if (rows.y == rows.x + 1) {
-                    bulk_g2s(d, src + (size_t)rows.x * raw_w, 2 * raw_w, &bars[b]);
-                } else {
-                    bulk_g2s(d, src + (size_t)rows.x * raw_w, raw_w, &bars[b]);
-                    bulk_g2s(d + raw_w, src + (size_t)rows.y * raw_w, raw_w, &bars[b]);
+
+    if (warp == kThreads / 32) {
+        // ------------------------------------------------------------------ producer warp
+        if (lane == 0) {
+            for (int it = 0; it < my_units; ++it) {
+                const int n = blockIdx.x + (it / units) * gridDim.x, part = it % units, st = it % kStages;
+                if (it >= kStages) mbar_wait(&empty[st], ((it / kStages) - 1) & 1);
+                const int fl = flags[n];
+                const int2 span = s_span[part];
+                const int nvalid = (fl & AGYM_FLAG_IDLE) ? 0 : __popc(fl & 3);
+                mbar_expect_tx(&full[st], (uint32_t)(nvalid * span.y));
+                if (nvalid) {
+                    uint8_t *dst = stages + st * stage_bytes;
+                    const size_t off = frame_bytes * n + (size_t)span.x * raw_w;
+                    if (fl & AGYM_FLAG_FRAME_A) bulk_g2s(dst, fa + off, span.y, &full[st]);
+                    if (fl & AGYM_FLAG_FRAME_B) bulk_g2s(dst + frame_stride, fb + off, span.y, &full[st]);
                 }
             }
         }
-    };
+        return;
+    }
 
-    // consumer constants: two adjacent output columns, a segment of the unit's rows
+    // ---------------------------------------------------------------------- consumer warps
     const int pairs = S_w >> 1, segs = kThreads / pairs;
     const int g = tid / pairs, pi = tid - g * pairs;
-    const bool worker = !producer && g < segs;
+    const bool worker = g < segs;
     const int4 px = worker ? __ldg(p.cx_pair + pi) : make_int4(0, 0, 0, 0);
     const int rows_per = (R + segs - 1) / segs;
     const int yy_begin = g * rows_per, yy_end = worker ? min(R, yy_begin + rows_per) : yy_begin;
-    // squeeze along W: one thread = one output column i (weights in registers), rows in passes
+    // squeeze along W: one thread = one output column i, rows in passes
     const int sq_rows = p.fast_squeeze ? kThreads / p.p_w : 0;
     const int sq_i = sq_rows ? tid % p.p_w : 0, sq_y0 = sq_rows ? tid / p.p_w : 0;
-    const bool sq_worker = pcache && sq_rows && !producer && sq_y0 < sq_rows;
+    const bool sq_worker = pcache && sq_rows && sq_y0 < sq_rows;
     const int nq = p.sqw_taps4 >> 2;
     const int2 sq_o = sq_worker ? __ldg(p.sqw_ofs + sq_i) : make_int2(0, 0);
     const float4 *sqw4 = reinterpret_cast<const float4 *>(s_sqw + sq_i * p.sqw_taps4);
 
-    if (producer && my_units > 0) issue(0);
     int slot = 0;
     for (int it = 0; it < my_units; ++it) {
-        const int n = blockIdx.x + (it / units) * gridDim.x, part = it % units, b = it & 1;
-        if (producer && it + 1 < my_units) issue(it + 1);  // buffer (it+1)&1 was released by the barrier below
+        const int n = blockIdx.x + (it / units) * gridDim.x, part = it % units, st = it % kStages;
         const int fl = flags[n];
         const bool idle = fl & AGYM_FLAG_IDLE;
         if (part == 0) slot = (head[n] + 1) % K;
-        if (worker && !idle) {
-            mbar_wait(&bars[b], (it >> 1) & 1);
-            const uint8_t *r = bufs + b * buf_bytes + px.x + yy_begin * pair_stride;
-            const int2 *ybs = s_ybs + part * R + yy_begin;
+        mbar_wait(&full[st], (it / kStages) & 1);
+        if (!idle && yy_begin < yy_end) {
+            const uint8_t *base = stages + st * stage_bytes + px.x;
+            const int4 *rw = s_row + part * R + yy_begin;
             uint8_t *o = s_frame + (part * R + yy_begin) * S_w + 2 * pi;
             if ((fl & 3) == 3) {  // both frames (the steady state)
 #pragma unroll 2
-                for (int yy = yy_begin; yy < yy_end; ++yy, r += pair_stride, ++ybs, o += S_w) {
-                    const int2 bs = *ybs;
-                    uint32_t m[2] = {0u, 0u};
+                for (int yy = yy_begin; yy < yy_end; ++yy, ++rw, o += S_w) {
+                    const int4 t = *rw;
+                    const uint8_t *ra = base + t.x, *rb = base + t.y;
+                    uint32_t m0 = 0u, m1 = 0u;
 #pragma unroll
                     for (int fr = 0; fr < 2; ++fr) {
-                        const uint8_t *r0 = r + fr * frame_unit;
-                        const uint32_t a0 = *reinterpret_cast<const uint32_t *>(r0);
-                        const uint32_t a1 = *reinterpret_cast<const uint32_t *>(r0 + 4);
-                        const uint32_t b0 = *reinterpret_cast<const uint32_t *>(r0 + raw_w);
-                        const uint32_t b1 = *reinterpret_cast<const uint32_t *>(r0 + raw_w + 4);
+                        const uint32_t a0 = *reinterpret_cast<const uint32_t *>(ra + fr * frame_stride);
+                        const uint32_t a1 = *reinterpret_cast<const uint32_t *>(ra + fr * frame_stride + 4);
+                        const uint32_t b0 = *reinterpret_cast<const uint32_t *>(rb + fr * frame_stride);
+                        const uint32_t b1 = *reinterpret_cast<const uint32_t *>(rb + fr * frame_stride + 4);
                         const uint32_t qa = __byte_perm(a0, a1, (uint32_t)px.y), qb = __byte_perm(b0, b1, (uint32_t)px.y);
                         const uint32_t h00 = __dp2a_lo((uint32_t)px.z, qa, 0u), h01 = __dp2a_hi((uint32_t)px.w, qa, 0u);
                         const uint32_t h10 = __dp2a_lo((uint32_t)px.z, qb, 0u), h11 = __dp2a_hi((uint32_t)px.w, qb, 0u);
-                        const uint32_t v0 = (__umulhi((uint32_t)bs.x, h00 >> 4) + __umulhi((uint32_t)bs.y, h10 >> 4) + 2u) >> 2;
-                        const uint32_t v1 = (__umulhi((uint32_t)bs.x, h01 >> 4) + __umulhi((uint32_t)bs.y, h11 >> 4) + 2u) >> 2;
-                        m[0] = max(m[0], v0);
-                        m[1] = max(m[1], v1);
+                        m0 = max(m0, (__umulhi((uint32_t)t.z, h00 >> 4) + __umulhi((uint32_t)t.w, h10 >> 4) + 2u) >> 2);
+                        m1 = max(m1, (__umulhi((uint32_t)t.z, h01 >> 4) + __umulhi((uint32_t)t.w, h11 >> 4) + 2u) >> 2);
                     }
-                    *reinterpret_cast<uint16_t *>(o) = (uint16_t)(min(m[0], 255u) | (min(m[1], 255u) << 8));
+                    *reinterpret_cast<uint16_t *>(o) = (uint16_t)(min(m0, 255u) | (min(m1, 255u) << 8));
                 }
             } else {  // resets / early game-over: one frame or none
-                for (int yy = yy_begin; yy < yy_end; ++yy, r += pair_stride, ++ybs, o += S_w) {
-                    const int2 bs = *ybs;
+                for (int yy = yy_begin; yy < yy_end; ++yy, ++rw, o += S_w) {
+                    const int4 t = *rw;
                     uint32_t m0 = 0u, m1 = 0u;
                     for (int fr = 0; fr < 2; ++fr) {
                         if (!(fl & (1 << fr))) continue;
-                        const uint8_t *r0 = r + fr * frame_unit;
-                        const uint32_t a0 = *reinterpret_cast<const uint32_t *>(r0);
-                        const uint32_t a1 = *reinterpret_cast<const uint32_t *>(r0 + 4);
-                        const uint32_t b0 = *reinterpret_cast<const uint32_t *>(r0 + raw_w);
-                        const uint32_t b1 = *reinterpret_cast<const uint32_t *>(r0 + raw_w + 4);
+                        const uint8_t *ra = base + t.x + fr * frame_stride, *rb = base + t.y + fr * frame_stride;
+                        const uint32_t a0 = *reinterpret_cast<const uint32_t *>(ra);
+                        const uint32_t a1 = *reinterpret_cast<const uint32_t *>(ra + 4);
+                        const uint32_t b0 = *reinterpret_cast<const uint32_t *>(rb);
+                        const uint32_t b1 = *reinterpret_cast<const uint32_t *>(rb + 4);
                         const uint32_t qa = __byte_perm(a0, a1, (uint32_t)px.y), qb = __byte_perm(b0, b1, (uint32_t)px.y);
                         const uint32_t h00 = __dp2a_lo((uint32_t)px.z, qa, 0u), h01 = __dp2a_hi((uint32_t)px.w, qa, 0u);
                         const uint32_t h10 = __dp2a_lo((uint32_t)px.z, qb, 0u), h11 = __dp2a_hi((uint32_t)px.w, qb, 0u);
-                        m0 = max(m0, (__umulhi((uint32_t)bs.x, h00 >> 4) + __umulhi((uint32_t)bs.y, h10 >> 4) + 2u) >> 2);
-                        m1 = max(m1, (__umulhi((uint32_t)bs.x, h01 >> 4) + __umulhi((uint32_t)bs.y, h11 >> 4) + 2u) >> 2);
+                        m0 = max(m0, (__umulhi((uint32_t)t.z, h00 >> 4) + __umulhi((uint32_t)t.w, h10 >> 4) + 2u) >> 2);
+                        m1 = max(m1, (__umulhi((uint32_t)t.z, h01 >> 4) + __umulhi((uint32_t)t.w, h11 >> 4) + 2u) >> 2);
                     }
                     *reinterpret_cast<uint16_t *>(o) = (uint16_t)(min(m0, 255u) | (min(m1, 255u) << 8));
                 }
             }
         }
-        __syncthreads();  // unit consumed: its buffer may be refilled; this part of s_frame is complete
-        if (part == units - 1 && !idle) {
-            if (tid == 0) head[n] = slot;
-            if (!producer) {
-                if (fl & AGYM_FLAG_HARD_RESET) {
-                    const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
-                    for (int k = 0; k < K; ++k) {
-                        if (k == slot) continue;
-                        uint4 *z = reinterpret_cast<uint4 *>(ring + ((size_t)n * K + k) * p.plane);
-                        for (int i = tid; i < p.plane / 16; i += kThreads) z[i] = z4;
-                        if (pcache) {
-                            float *zc = pcache + ((size_t)n * K + k) * p.p_h * p.p_w;
-                            for (int i = tid; i < p.p_h * p.p_w; i += kThreads) zc[i] = 0.f;
-                        }
-                    }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[st]);  // this warp is done with the stage
+        if (part != units - 1 || idle) continue;
+
+        consumer_sync();  // the whole 84x84 frame is in s_frame
+        if (tid == 0) head[n] = slot;
+        if (fl & AGYM_FLAG_HARD_RESET) {
+            const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
+            for (int k = 0; k < K; ++k) {
+                if (k == slot) continue;
+                uint4 *z = reinterpret_cast<uint4 *>(ring + ((size_t)n * K + k) * p.plane);
+                for (int i = tid; i < p.plane / 16; i += kThreads) z[i] = z4;
+                if (pcache) {
+                    float *zc = pcache + ((size_t)n * K + k) * p.p_h * p.p_w;
+                    for (int i = tid; i < p.p_h * p.p_w; i += kThreads) zc[i] = 0.f;
                 }
-                uint4 *out4 = reinterpret_cast<uint4 *>(ring + ((size_t)n * K + slot) * p.plane);
-                for (int i = tid; i < p.plane / 16; i += kThreads) out4[i] = reinterpret_cast<const uint4 *>(s_frame)[i];
             }
-            if (pcache) {  // uniform
-                if (sq_rows) {
-                    if (sq_worker) {
-                        for (int y = sq_y0; y < p.S_h; y += sq_rows) {
-                            const uint32_t *src = reinterpret_cast<const uint32_t *>(s_frame + y * S_w + sq_o.x);
-                            const uint32_t w0 = src[0], w1 = src[1], w2 = src[2], w3 = src[3];
-                            const uint32_t a[4] = {__funnelshift_r(w0, w1, sq_o.y), __funnelshift_r(w1, w2, sq_o.y),
-                                                   __funnelshift_r(w2, w3, sq_o.y), w3 >> sq_o.y};
-                            float acc = 0.f;
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                if (q < nq) {
-                                    const uint32_t v = a[q];
-                                    const float4 w = sqw4[q];
-                                    acc = fmaf(w.x, (float)(v & 0xffu), acc);
-                                    acc = fmaf(w.y, (float)((v >> 8) & 0xffu), acc);
-                                    acc = fmaf(w.z, (float)((v >> 16) & 0xffu), acc);
-                                    acc = fmaf(w.w, (float)(v >> 24), acc);
-                                }
-                            }
-                            s_t1[y * p.p_w + sq_i] = acc;
-                        }
-                    }
-                } else if (!producer) {
-                    resample_w<uint8_t>(s_frame, S_w, s_t1, p.p_w, p.S_h, p.sq_w, tid, kThreads);
-                }
-                __syncthreads();
-                if (!producer)
-                    resample_h<float>(s_t1, p.p_w, pcache + ((size_t)n * K + slot) * p.p_h * p.p_w, p.p_w, p.p_w, p.sq_h, tid,
-                                      kThreads);
-            }
-            __syncthreads();  // s_frame / s_t1 are reused by the next env
         }
+        uint4 *out4 = reinterpret_cast<uint4 *>(ring + ((size_t)n * K + slot) * p.plane);
+        for (int i = tid; i < p.plane / 16; i += kThreads) out4[i] = reinterpret_cast<const uint4 *>(s_frame)[i];
+        if (pcache) {  // uniform
+            if (sq_rows) {
+                if (sq_worker) {
+                    for (int y = sq_y0; y < p.S_h; y += sq_rows) {
+                        const uint32_t *src = reinterpret_cast<const uint32_t *>(s_frame + y * S_w + sq_o.x);
+                        const uint32_t w0 = src[0], w1 = src[1], w2 = src[2], w3 = src[3];
+                        const uint32_t a[4] = {__funnelshift_r(w0, w1, sq_o.y), __funnelshift_r(w1, w2, sq_o.y),
+                                               __funnelshift_r(w2, w3, sq_o.y), w3 >> sq_o.y};
+                        float acc = 0.f;
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            if (q < nq) {
+                                const uint32_t v = a[q];
+                                const float4 w = sqw4[q];
+                                acc = fmaf(w.x, (float)(v & 0xffu), acc);
+                                acc = fmaf(w.y, (float)((v >> 8) & 0xffu), acc);
+                                acc = fmaf(w.z, (float)((v >> 16) & 0xffu), acc);
+                                acc = fmaf(w.w, (float)(v >> 24), acc);
+                            }
+                        }
+                        s_t1[y * p.p_w + sq_i] = acc;
+                    }
+                }
+            } else {
+                resample_w<uint8_t>(s_frame, S_w, s_t1, p.p_w, p.S_h, p.sq_w, tid, kThreads);
+            }
+            consumer_sync();
+            resample_h<float>(s_t1, p.p_w, pcache + ((size_t)n * K + slot) * p.p_h * p.p_w, p.p_w, p.p_w, p.sq_h, tid, kThreads);
+        }
+        consumer_sync();  // s_frame / s_t1 are reused by the next env
     }
 }
 
@@ -1190,12 +1196,14 @@ cudaError_t launch_ingest_atari(const DevPlan &p, const uint8_t *fa, const uint8
     size_t smem = a16(sizeof(int32_t) * 3 * (p.S_w + p.S_h)) + a16(2 * (size_t)2 * p.S_h * p.raw_w);
     if (pcache) smem += a16(p.plane) + sizeof(float) * p.S_h * p.p_w;
     cudaError_t e;
-    if (p.fast_ingest && p.raw_c == 1 && !g_disable_tma) {
-        int units = g_units ? g_units : 3;
-        while (units > 1 && p.S_h % units != 0) --units;
-        const int R = p.S_h / units;
-        const size_t frame_unit = (size_t)R * (2 * p.raw_w + 16);
-        size_t fs = 2 * a16(2 * frame_unit + 16) + a16(p.plane + 16) + 16 * (size_t)p.S_h;
+    int ui = std::min(std::max(g_units ? g_units : 3, 1), 4);  // units per env: index into the plan's span table
+    while (ui > 1 && p.tma_span_rows[ui - 1] == 0) --ui;
+    if (p.tma_span_rows[ui - 1] == 0)
+        for (ui = 4; ui > 1 && p.tma_span_rows[ui - 1] == 0;) --ui;
+    if (p.fast_ingest && p.raw_c == 1 && !g_disable_tma && p.tma_span_rows[ui - 1] > 0) {
+        const int units = ui, span_rows = p.tma_span_rows[ui - 1];
+        const size_t stage = a16(2 * ((size_t)span_rows * p.raw_w + 16));
+        size_t fs = 2 * stage + a16(p.plane + 16) + 16 * (size_t)p.S_h + 8 * (size_t)((units + 1) & ~1);
         if (pcache) fs += sizeof(float) * ((size_t)p.S_h * p.p_w + (size_t)p.p_w * 16);
         int dev = 0, sms = 148, occ = 1;
         cudaGetDevice(&dev);
@@ -1205,13 +1213,10 @@ cudaError_t launch_ingest_atari(const DevPlan &p, const uint8_t *fa, const uint8
         if ((e = set_smem(k_ingest_atari_tma<__VA_ARGS__>, fs)) != cudaSuccess) return e;                           \
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_ingest_atari_tma<__VA_ARGS__>, kIngestThreads, fs);   \
         k_ingest_atari_tma<__VA_ARGS__><<<std::min(p.N, sms * std::max(occ, 1)), kIngestThreads, fs, st>>>(         \
-            p, fa, fb, flags, ring, head, pcache, units);                                                           \
+            p, fa, fb, flags, ring, head, pcache, units, span_rows);                                                \
     }
-        const bool std_geom = p.raw_w == 160 && p.S_w == 84;
-        if (std_geom && R == 42) AGYM_LAUNCH_TMA(160, 84, 42)
-        else if (std_geom && R == 28) AGYM_LAUNCH_TMA(160, 84, 28)
-        else if (std_geom && R == 21) AGYM_LAUNCH_TMA(160, 84, 21)
-        else AGYM_LAUNCH_TMA(0, 0, 0)
+        if (p.raw_w == 160 && p.S_w == 84) AGYM_LAUNCH_TMA(160, 84)
+        else AGYM_LAUNCH_TMA(0, 0)
 #undef AGYM_LAUNCH_TMA
         return cudaGetLastError();
     }

@@ -41,6 +41,7 @@ struct DevPlan {
     // ingest: per output-column pair {byte offset of the aligned word, PRMT selector, coef(x0), coef(x0+1)}
     // and per output row {b0 << 16, b1 << 16} (atari_env.py:74 fixed-point bilinear, dp2a form)
     int32_t fast_ingest;
+    int32_t tma_span_rows[4];  // TMA ingest: largest source-row span of a unit when an env is cut into 1..4 units (0 = n/a)
     const int4 *cx_pair;    // [S_w / 2]
     const int2 *cy_bs;      // [S_h]
     // squeeze along W from u8 rows: per output column {aligned byte offset, shift, first weight index}
