@@ -420,9 +420,11 @@ __device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier
 __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+template <bool BACKOFF = false>
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     uint32_t done = 0;
     while (!done) {
+        if (BACKOFF) __nanosleep(200);  // a lone producer lane must not burn issue slots while it waits
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
@@ -506,9 +508,9 @@ __global__ void __launch_bounds__(kIngestThreads, 3) k_ingest_atari_tma(const __
     if (warp == kThreads / 32) {
         // ------------------------------------------------------------------ producer warp
         if (lane == 0) {
+            int n = blockIdx.x, part = 0, st = 0, ph = 1;  // ph: parity of the empty-barrier phase to wait for
             for (int it = 0; it < my_units; ++it) {
-                const int n = blockIdx.x + (it / units) * gridDim.x, part = it % units, st = it % kStages;
-                if (it >= kStages) mbar_wait(&empty[st], ((it / kStages) - 1) & 1);
+                if (it >= kStages) mbar_wait<true>(&empty[st], ph);
                 const int fl = flags[n];
                 const int2 span = s_span[part];
                 const int nvalid = (fl & AGYM_FLAG_IDLE) ? 0 : __popc(fl & 3);
@@ -519,6 +521,8 @@ __global__ void __launch_bounds__(kIngestThreads, 3) k_ingest_atari_tma(const __
                     if (fl & AGYM_FLAG_FRAME_A) bulk_g2s(dst, fa + off, span.y, &full[st]);
                     if (fl & AGYM_FLAG_FRAME_B) bulk_g2s(dst + frame_stride, fb + off, span.y, &full[st]);
                 }
+                if (++part == units) { part = 0; n += gridDim.x; }
+                if (++st == kStages) { st = 0; ph ^= 1; }
             }
         }
         return;
@@ -539,13 +543,15 @@ __global__ void __launch_bounds__(kIngestThreads, 3) k_ingest_atari_tma(const __
     const int2 sq_o = sq_worker ? __ldg(p.sqw_ofs + sq_i) : make_int2(0, 0);
     const float4 *sqw4 = reinterpret_cast<const float4 *>(s_sqw + sq_i * p.sqw_taps4);
 
-    int slot = 0;
-    for (int it = 0; it < my_units; ++it) {
-        const int n = blockIdx.x + (it / units) * gridDim.x, part = it % units, st = it % kStages;
-        const int fl = flags[n];
+    int slot = 0, fl = 0;
+    for (int it = 0, n = blockIdx.x, part = 0, st = 0, ph = 0; it < my_units; ++it) {
+        if (part == 0) {
+            fl = flags[n];
+            slot = head[n] + 1;
+            slot -= slot >= K ? K : 0;
+        }
         const bool idle = fl & AGYM_FLAG_IDLE;
-        if (part == 0) slot = (head[n] + 1) % K;
-        mbar_wait(&full[st], (it / kStages) & 1);
+        mbar_wait(&full[st], ph);
         if (!idle && yy_begin < yy_end) {
             const uint8_t *base = stages + st * stage_bytes + px.x;
             const int4 *rw = s_row + part * R + yy_begin;
@@ -593,8 +599,14 @@ __global__ void __launch_bounds__(kIngestThreads, 3) k_ingest_atari_tma(const __
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[st]);  // this warp is done with the stage
-        if (part != units - 1 || idle) continue;
-
+        if (++st == kStages) { st = 0; ph ^= 1; }
+        if (++part < units) continue;
+        part = 0;
+        const int n_done = n;
+        n += gridDim.x;
+        if (idle) continue;
+        {
+            const int n = n_done;
         consumer_sync();  // the whole 84x84 frame is in s_frame
         if (tid == 0) head[n] = slot;
         if (fl & AGYM_FLAG_HARD_RESET) {
@@ -641,6 +653,7 @@ __global__ void __launch_bounds__(kIngestThreads, 3) k_ingest_atari_tma(const __
             resample_h<float>(s_t1, p.p_w, pcache + ((size_t)n * K + slot) * p.p_h * p.p_w, p.p_w, p.p_w, p.sq_h, tid, kThreads);
         }
         consumer_sync();  // s_frame / s_t1 are reused by the next env
+        }
     }
 }
 
