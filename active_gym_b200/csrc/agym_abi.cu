@@ -345,6 +345,25 @@ int agym_observe_flexible(const agym_plan *plan, const uint8_t *d_ring, const in
                                        pad_h, pad_w, d_out, as_stream(stream)));
 }
 
+int agym_table_cv2(int n_src, int n_dst, int zero_frac_at_border, int32_t *h_s0, int32_t *h_s1, int32_t *h_coef) {
+    if (n_src <= 0 || n_dst <= 0 || !h_s0 || !h_s1 || !h_coef) return AGYM_ERR_INVALID_ARG;
+    const Cv2Axis ax = build_cv2_axis(n_src, n_dst, zero_frac_at_border != 0);
+    std::memcpy(h_s0, ax.s0.data(), sizeof(int32_t) * n_dst);
+    std::memcpy(h_s1, ax.s1.data(), sizeof(int32_t) * n_dst);
+    std::memcpy(h_coef, ax.coef.data(), sizeof(int32_t) * n_dst);
+    return AGYM_OK;
+}
+
+int agym_table_aa(int n_in, int n_out, int32_t *h_xmin, float *h_w, size_t w_capacity, int32_t *taps) {
+    if (n_in <= 0 || n_out <= 0 || !h_xmin || !h_w || !taps) return AGYM_ERR_INVALID_ARG;
+    const AaAxis ax = build_aa_axis(n_in, n_out);
+    if (ax.w.size() > w_capacity) return AGYM_ERR_INVALID_ARG;
+    std::memcpy(h_xmin, ax.xmin.data(), sizeof(int32_t) * n_out);
+    std::memcpy(h_w, ax.w.data(), sizeof(float) * ax.w.size());
+    *taps = ax.taps;
+    return AGYM_OK;
+}
+
 int agym_synth_frames(uint8_t *d_dst, size_t n_bytes, uint64_t seed, void *stream) {
     if (!d_dst || n_bytes % 16 != 0) return AGYM_ERR_INVALID_ARG;
     return ret(launch_synth(d_dst, n_bytes, seed, as_stream(stream)));

@@ -140,6 +140,14 @@ AGYM_API int agym_observe_flexible(const agym_plan *plan, const uint8_t *d_ring,
                           int32_t *d_loc, int32_t *d_res, int variant, int pad_h, int pad_w,
                           uint8_t *d_out, void *stream);
 
+/* Host-only: the coefficient tables a plan would upload, for inspection and CPU-side tests.
+ * agym_table_cv2: OpenCV INTER_LINEAR 11-bit coefficients of one axis (atari_env.py:74);
+ * out arrays have n_dst entries, coef = c0 | (c1 << 16).
+ * agym_table_aa: ATen antialiased-bilinear weights of one axis (fov_env.py:120,248,278,366-368);
+ * h_xmin has n_out entries, h_w has n_out * (*taps) entries (capacity w_capacity floats). */
+AGYM_API int agym_table_cv2(int n_src, int n_dst, int zero_frac_at_border, int32_t *h_s0, int32_t *h_s1, int32_t *h_coef);
+AGYM_API int agym_table_aa(int n_in, int n_out, int32_t *h_xmin, float *h_w, size_t w_capacity, int32_t *taps);
+
 /* Benchmark / test helper: fills d_dst with a counter-based hash of (seed, byte index). */
 AGYM_API int agym_synth_frames(uint8_t *d_dst, size_t n_bytes, uint64_t seed, void *stream);
 
