@@ -1,0 +1,20 @@
+#!/bin/bash
+# One GPU-box pass: parity tests, smoke, every bench line, then the ncu launch list and one full capture.
+set -u
+O=gpurun_out
+TAG=${1:-r1}
+python -m pytest tests -m gpu -x -q > $O/pytest_gpu_$TAG.log 2>&1; echo "pytest rc=$?" | tee -a $O/pytest_gpu_$TAG.log
+python -c "import __graft_entry__ as g; g.smoke()" > $O/smoke_$TAG.log 2>&1; echo "smoke rc=$?" | tee -a $O/smoke_$TAG.log
+python bench.py > $O/bench_${TAG}_default.json 2> $O/bench_${TAG}_default.err; echo "bench rc=$?"
+python bench.py --impl reference --steps 5 --warmup 1 > $O/bench_${TAG}_reference.json 2> $O/bench_${TAG}_reference.err; echo "ref rc=$?"
+for w in atari_fixed atari_flexible dmc_fixed; do
+  python bench.py --workload $w --steps 30 > $O/bench_${TAG}_$w.json 2> $O/bench_${TAG}_$w.err; echo "$w rc=$?"
+done
+CMD="python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e"
+$CMD > $O/plain_$TAG.log 2>&1 &&
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches_$TAG.csv $CMD > $O/ncu_l_$TAG.log 2>&1
+echo "ncu launches rc=$?"
+$CMD > $O/plain_$TAG.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:'k_ingest_atari_tma|k_observe_peripheral_fast' -s 8 -c 4 -f -o $O/prof_$TAG $CMD > $O/ncu_f_$TAG.log 2>&1
+echo "ncu full rc=$?"
+tail -c 600 $O/bench_${TAG}_default.json
