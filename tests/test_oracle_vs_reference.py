@@ -67,12 +67,12 @@ def _drive_atari(cls_name, seed, *, mode, variant="crop", periph=None, flexible=
     for i in range(steps):
         atype = int(rng.integers(0, 2)) if flexible else 0
         if atype == 1:
-            a = rng.integers(20, 51, 2).astype(np.float64)
+            a = rng.integers(20, 51, 2)  # integer dtype: the reference slices with fov_res unvalidated (fov_env.py:284,323)
         elif mode == "relative":
             a = rng.uniform(-14, 14, 2) if i % 3 else rng.integers(-10, 11, 2) + 0.5
         else:
             a = rng.uniform(-5, 70, 2) if i % 3 else rng.integers(0, 55, 2) + 0.5
-        act = {"motor_action": 0, "sensory_action": torch.tensor(a) if i % 2 else a}
+        act = {"motor_action": 0, "sensory_action": torch.tensor(a) if (i % 2 and atype == 0) else a}
         if flexible:
             act["sensory_action_type"] = atype
         n0 = len(script.log)
@@ -80,7 +80,7 @@ def _drive_atari(cls_name, seed, *, mode, variant="crop", periph=None, flexible=
         idx = script.log[n0:]
         assert len(idx) == 2 and not done
         orc.ingest_atari(screens[idx[0], :, :, 0][None], screens[idx[1], :, :, 0][None], np.array([FA | FB], np.uint8), ring, head)
-        orc.update_loc(a, loc, obs_size=S, fov_size=fov, relative=(mode == "relative"), lo=-10.0, hi=10.0,
+        orc.update_loc(np.asarray(a, np.float64), loc, obs_size=S, fov_size=fov, relative=(mode == "relative"), lo=-10.0, hi=10.0,
                        atype=np.array([atype]) if flexible else None, res=res if flexible else None)
         check(obs, info)
 
@@ -127,6 +127,6 @@ def test_dmc_live():
         n0 = len(script.log)
         obs, _, _, _, info = env.step({"motor_action": np.zeros(2, np.float32), "sensory_action": a})
         orc.ingest_dmc(screens[script.log[n0:][-1]][None], np.array([FA], np.uint8), ring, head)
-        orc.update_loc(a, loc, obs_size=S, fov_size=fov)
+        orc.update_loc(np.asarray(a, np.float64), loc, obs_size=S, fov_size=fov)
         assert np.array_equal(info["fov_loc"], loc[0])
         assert np.array_equal(orc.observe_fixed(ring, head, loc, fov)[0], _u8_exact(obs))
