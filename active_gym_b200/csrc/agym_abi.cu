@@ -15,6 +15,7 @@ using namespace agym;
 struct agym_plan {
     agym_config cfg;
     DevPlan dev;
+    ExpandStd expand_std;  // host copy, see agym_kernels.cuh
     void *pool = nullptr;  // device: every coefficient table, one allocation
     size_t pool_bytes = 0;
     int device = -1;
@@ -185,9 +186,9 @@ int agym_plan_create(const agym_config *cfg, agym_plan **out_plan) {
     }
     // expand p -> S as two-tap lerps (plain bilinear upsampling: antialiasing is inactive)
     bool fast_expand = c.periph_h > 0 && c.periph_h < c.obs_h && c.periph_w < c.obs_w && c.periph_h >= 2 && c.periph_w >= 2;
-    size_t o_ewi = 0, o_eww = 0, o_ehi = 0, o_ehw = 0;
+    size_t o_ewi = 0, o_eww = 0, o_ehi = 0, o_ehw = 0, o_eww1 = 0;
     if (fast_expand) {
-        auto lerp = [&](int n_in, int n_out, std::vector<int32_t> &i0, std::vector<float> &w0) {
+        auto lerp = [&](int n_in, int n_out, std::vector<int32_t> &i0, std::vector<float> &w0, std::vector<float> &w1) {
             const AaAxis ax = build_aa_axis(n_in, n_out);
             for (int i = 0; i < n_out; ++i) {
                 int first = -1, last = -1;
@@ -195,16 +196,38 @@ int agym_plan_create(const agym_config *cfg, agym_plan **out_plan) {
                     if (ax.w[static_cast<size_t>(i) * ax.taps + j] != 0.f) { if (first < 0) first = j; last = j; }
                 if (first < 0 || last - first > 1) { fast_expand = false; return; }
                 const int a = ax.xmin[i] + first;
-                if (last > first) { i0.push_back(a); w0.push_back(ax.w[static_cast<size_t>(i) * ax.taps + first]); }
-                else if (a + 1 <= n_in - 1) { i0.push_back(a); w0.push_back(1.f); }
-                else { i0.push_back(a - 1); w0.push_back(0.f); }
+                if (last > first) {
+                    i0.push_back(a);
+                    w0.push_back(ax.w[static_cast<size_t>(i) * ax.taps + first]);
+                    w1.push_back(ax.w[static_cast<size_t>(i) * ax.taps + last]);
+                }
+                else if (a + 1 <= n_in - 1) { i0.push_back(a); w0.push_back(1.f); w1.push_back(0.f); }
+                else { i0.push_back(a - 1); w0.push_back(0.f); w1.push_back(1.f); }
             }
         };
         std::vector<int32_t> wi, hi;
-        std::vector<float> ww, hw;
-        lerp(c.periph_w, c.obs_w, wi, ww);
-        if (fast_expand) lerp(c.periph_h, c.obs_h, hi, hw);
-        if (fast_expand) { o_ewi = pool.add_i(wi); o_eww = pool.add_f(ww); o_ehi = pool.add_i(hi); o_ehw = pool.add_f(hw); }
+        std::vector<float> ww, hw, ww1, hw1;
+        lerp(c.periph_w, c.obs_w, wi, ww, ww1);
+        if (fast_expand) lerp(c.periph_h, c.obs_h, hi, hw, hw1);
+        if (fast_expand) {
+            o_ewi = pool.add_i(wi); o_eww = pool.add_f(ww); o_eww1 = pool.add_f(ww1);
+            o_ehi = pool.add_i(hi); o_ehw = pool.add_f(hw);
+            // standard geometry: do the tables follow k_observe_peripheral_std's compile-time pattern,
+            // i0 = clamp(floor((40 i - 64) / 168), 0, 18) with single-tap borders on both axes?
+            ExpandStd &es = pl->expand_std;
+            bool ok = c.obs_h == 84 && c.obs_w == 84 && c.periph_h == 20 && c.periph_w == 20;
+            for (int i = 0; ok && i < 84; ++i) {
+                const int raw = (40 * i - 64 + 168 * 4) / 168 - 4;
+                const int want = raw < 0 ? 0 : (raw > 18 ? 18 : raw);
+                ok = wi[i] == want && hi[i] == want;
+                if (raw < 0) ok = ok && ww[i] == 1.f && hw[i] == 1.f;       // out = t[0]
+                if (raw > 18) ok = ok && ww[i] == 0.f && hw[i] == 0.f;      // out = t[19]
+            }
+            if (ok) {
+                for (int i = 0; i < 84; ++i) { es.w0[i] = ww[i]; es.w1[i] = ww1[i]; }
+            }
+            es.ok = ok;
+        }
     }
 
     pl->pool_bytes = pool.words.size() * 4;
@@ -265,6 +288,7 @@ int agym_plan_create(const agym_config *cfg, agym_plan **out_plan) {
     if (fast_expand) {
         d.exw_i0 = ip(o_ewi); d.exw_w0 = reinterpret_cast<const float *>(base + o_eww);
         d.exh_i0 = ip(o_ehi); d.exh_w0 = reinterpret_cast<const float *>(base + o_ehw);
+        d.exw_w1 = reinterpret_cast<const float *>(base + o_eww1);
     }
     *out_plan = pl;
     return AGYM_OK;
@@ -331,7 +355,7 @@ int agym_observe_peripheral(const agym_plan *plan, const uint8_t *d_ring, const 
     const int v = check_fov_args(plan, d_ring, d_head, d_action, d_fov_ctrl, d_loc, d_out);
     if (v != AGYM_OK) return v;
     if (plan->cfg.periph_h == 0) return AGYM_ERR_INVALID_ARG;
-    return ret(launch_observe_peripheral(plan->dev, d_ring, d_head, d_pcache, d_action, d_fov_ctrl, d_loc, d_out, as_stream(stream)));
+    return ret(launch_observe_peripheral(plan->dev, &plan->expand_std, d_ring, d_head, d_pcache, d_action, d_fov_ctrl, d_loc, d_out, as_stream(stream)));
 }
 
 int agym_observe_flexible(const agym_plan *plan, const uint8_t *d_ring, const int32_t *d_head, const double *d_action,

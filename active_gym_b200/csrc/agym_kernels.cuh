@@ -48,10 +48,19 @@ struct DevPlan {
     int32_t fast_squeeze, sqw_taps4;  // taps padded to a multiple of 4
     const int2 *sqw_ofs;    // [p_w] {aligned byte offset, 8 * (xmin & 3)}
     const float *sqw_w;     // [p_w][sqw_taps4]
-    // expand p -> S as two-tap lerps: out = t[i0+1] + w0 * (t[i0] - t[i0+1])
+    // expand p -> S as two taps: out = w0 * t[i0] + w1 * t[i0+1]  (w1 is given along W only)
     int32_t fast_expand;
     const int32_t *exw_i0, *exh_i0;   // [S_w], [S_h]
-    const float *exw_w0, *exh_w0;
+    const float *exw_w0, *exh_w0, *exw_w1;
+};
+
+// Host-side copy of the W-expand weights of the standard geometry (obs 84, periphery 20); passed
+// to k_observe_peripheral_std by value so that they sit in the constant bank.  ok = the plan's
+// tables follow the compile-time tap pattern of that kernel.
+struct ExpandStd {
+    float w0[84];
+    float w1[84];
+    int32_t ok;
 };
 
 cudaError_t launch_ingest_atari(const DevPlan &p, const uint8_t *fa, const uint8_t *fb, const uint8_t *flags,
@@ -61,9 +70,9 @@ cudaError_t launch_ingest_dmc(const DevPlan &p, const uint8_t *f, const uint8_t 
 cudaError_t launch_stack(const DevPlan &p, const uint8_t *ring, const int32_t *head, uint8_t *out, cudaStream_t st);
 cudaError_t launch_observe_fixed(const DevPlan &p, const uint8_t *ring, const int32_t *head, const double *action,
                                  const uint8_t *ctrl, int32_t *loc, int variant, uint8_t *out, cudaStream_t st);
-cudaError_t launch_observe_peripheral(const DevPlan &p, const uint8_t *ring, const int32_t *head, const float *pcache,
-                                      const double *action, const uint8_t *ctrl, int32_t *loc, uint8_t *out,
-                                      cudaStream_t st);
+cudaError_t launch_observe_peripheral(const DevPlan &p, const ExpandStd *ew, const uint8_t *ring, const int32_t *head,
+                                      const float *pcache, const double *action, const uint8_t *ctrl, int32_t *loc,
+                                      uint8_t *out, cudaStream_t st);
 cudaError_t launch_observe_flexible(const DevPlan &p, const uint8_t *ring, const int32_t *head, const double *action,
                                     const int32_t *atype, const uint8_t *ctrl, int32_t *loc, int32_t *res, int variant,
                                     int pad_h, int pad_w, uint8_t *out, cudaStream_t st);
