@@ -50,19 +50,31 @@ __device__ __forceinline__ uint32_t quant_u8(float v) {
     return (uint32_t)min(max(q, 0), 255);
 }
 
-// fov_loc update of the fixed fovea (fov_env.py:187-199).  STORE: write the new loc back
-// (one thread per env); otherwise only compute it.
-template <bool STORE = true>
-__device__ __forceinline__ void update_loc_fixed(const DevPlan &p, int n, const double *action, const uint8_t *ctrl,
-                                                 int32_t *loc, int &r, int &c) {
-    const int mode = ctrl ? ctrl[n] : AGYM_FOV_APPLY;
-    r = loc[2 * n];
-    c = loc[2 * n + 1];
-    if (mode == AGYM_FOV_RESET) {
+// fov_loc update of the fixed fovea (fov_env.py:187-199), split into the global loads and the
+// arithmetic so that a persistent kernel can issue the loads one env ahead.
+struct LocIn {
+    double a0, a1;
+    int r, c, mode;
+};
+
+__device__ __forceinline__ LocIn load_loc_in(int n, const double *action, const uint8_t *ctrl, const int32_t *loc) {
+    LocIn v;
+    v.mode = ctrl ? ctrl[n] : AGYM_FOV_APPLY;
+    v.r = loc[2 * n];
+    v.c = loc[2 * n + 1];
+    v.a0 = action ? action[2 * n] : 0.0;
+    v.a1 = action ? action[2 * n + 1] : 0.0;
+    return v;
+}
+
+__device__ __forceinline__ void apply_loc(const DevPlan &p, const LocIn &v, int &r, int &c) {
+    r = v.r;
+    c = v.c;
+    if (v.mode == AGYM_FOV_RESET) {
         r = p.init_r;
         c = p.init_c;
-    } else if (mode == AGYM_FOV_APPLY) {
-        double a0 = action[2 * n], a1 = action[2 * n + 1];
+    } else if (v.mode == AGYM_FOV_APPLY) {
+        double a0 = v.a0, a1 = v.a1;
         if (p.relative) {
             a0 = (double)(r + clip_rint(a0, p.lo, p.hi));
             a1 = (double)(c + clip_rint(a1, p.lo, p.hi));
@@ -70,6 +82,13 @@ __device__ __forceinline__ void update_loc_fixed(const DevPlan &p, int n, const 
         r = clip_rint(a0, 0.0, (double)(p.S_h - p.f_h));
         c = clip_rint(a1, 0.0, (double)(p.S_w - p.f_w));
     }
+}
+
+// STORE: write the new loc back (one thread per env); otherwise only compute it.
+template <bool STORE = true>
+__device__ __forceinline__ void update_loc_fixed(const DevPlan &p, int n, const double *action, const uint8_t *ctrl,
+                                                 int32_t *loc, int &r, int &c) {
+    apply_loc(p, load_loc_in(n, action, ctrl, loc), r, c);
     if (STORE) {
         loc[2 * n] = r;
         loc[2 * n + 1] = c;
@@ -1109,19 +1128,20 @@ __global__ void __launch_bounds__(128) k_observe_peripheral_v2(const __grid_cons
 // tables against this pattern before the kernel is used; the WEIGHTS always come from the
 // host tables (ATen's values), never from device arithmetic.
 //
-// Warp-specialised, one barrier per env:
-//   B threads  (21 quads x K frames x 4 row segments) H-expand + quantise + paste + store env e
-//              from T[it & 1];
-//   A threads  (K x 20, one per squeezed row) prefetch env e+2 (cp.async: cached squeeze + fovea
-//              words, triple buffered) and W-expand env e+1 into T[(it + 1) & 1] meanwhile;
-//              A thread 0 also applies the sensory action of env e+3 to fov_loc.
+// Warp-specialised, one barrier per env (iteration `it` of a CTA handles env e = blockIdx.x + it * G):
+//   B threads  (21 quads x K frames x 4 row segments) issue the cp.async prefetch of env e+3 (cached
+//              squeeze + ring words under its fovea; 4 buffers in flight), then H-expand + quantise
+//              + paste + store env e from T[it & 1];
+//   A threads  (K x 20, one per squeezed row) W-expand env e+1 into T[(it + 1) & 1] meanwhile.
+//              Every 32 iterations A warp 0 applies the sensory actions of the CTA's next 32 envs
+//              to fov_loc, one env per lane (fov_env.py:187-199), a batch ahead of their use.
 struct StdGeom {
     static constexpr int S = 84, P = 20, Q = 21, SEG = 4, R = 21, SPAN = 7;
     // floor((40 i - 64) / 168): source index of output i relative to the 20-sample axis
     __host__ __device__ static constexpr int src(int i) { return (40 * i - 64 + 168 * 4) / 168 - 4; }
 };
 
-template <int K, int NW>  // NW: words per staged fovea row ((f_w + 3) / 4 + 1) when known at compile time, else 0
+template <int K>
 __global__ void __launch_bounds__((((StdGeom::Q * StdGeom::SEG * K + 31) / 32) + ((StdGeom::P * K + 31) / 32)) * 32, 2)
     k_observe_peripheral_std(const __grid_constant__ DevPlan p, const __grid_constant__ ExpandStd ew,
                              const uint8_t *__restrict__ ring, const int32_t *__restrict__ head,
@@ -1129,63 +1149,43 @@ __global__ void __launch_bounds__((((StdGeom::Q * StdGeom::SEG * K + 31) / 32) +
                              const uint8_t *__restrict__ ctrl, int32_t *__restrict__ loc, uint8_t *__restrict__ out) {
     using Gm = StdGeom;
     constexpr int S = Gm::S, P = Gm::P, Q = Gm::Q, R = Gm::R;
-    constexpr int NB = Q * Gm::SEG * K, NBW = (NB + 31) / 32;      // B threads / warps
-    constexpr int NA = P * K, NAW = (NA + 31) / 32;                // A threads / warps
+    constexpr int NB = Q * Gm::SEG * K, NBW = (NB + 31) / 32, NBT = NBW * 32;  // B threads / warps / incl. idle lanes
+    constexpr int NA = P * K;                                                  // A threads
     constexpr int PP = P * P, PLANE_W = S * S / 4;
     constexpr int T_FLOATS = K * P * S;
+    constexpr int NBUF = 4, LOC_RING = 64;
     extern __shared__ __align__(16) uint8_t smem[];
-    __shared__ int s_loc[4][2];
+    __shared__ int s_loc[LOC_RING][2];
     const int tid = threadIdx.x;
     const int N = p.N, f_h = p.f_h, G = gridDim.x;
-    const int nw_max = NW ? NW : (p.f_w + 3) / 4 + 1;
-    const int fov_words = (K * f_h * nw_max + 3) & ~3;
-    const int buf_words = K * PP + fov_words;
+    const int nw_max = (p.f_w + 3) / 4 + 1;
+    const int fov_n = K * f_h * nw_max;                              // staged fovea words per env
+    const int buf_words = K * PP + ((fov_n + 3) & ~3);
     float *s_T = reinterpret_cast<float *>(smem);                    // [2][K][P][S], biased
-    float *bufs = s_T + 2 * T_FLOATS;                                // [3]{ sq [K][P][P] | fov [K][f_h][nw_max] }
-    float *s_hw = bufs + 3 * buf_words;                              // [SEG][24] H weights (w0) per segment row
+    float *bufs = s_T + 2 * T_FLOATS;                                // [NBUF]{ sq [K][P][P] | fov [K][f_h][nw_max] }
+    float *s_hw = bufs + NBUF * buf_words;                           // [SEG][24] H weights (w0) per segment row
     const uint32_t *ring_w = reinterpret_cast<const uint32_t *>(ring);
 
     for (int i = tid; i < Gm::SEG * 24; i += blockDim.x) {
         const int g = i / 24, r = i - g * 24;
         s_hw[i] = r < R ? __ldg(p.exh_w0 + g * R + r) : 0.f;
     }
-    if (tid == NBW * 32) {  // A thread 0: fov_loc of this CTA's first three envs
-        for (int j = 0; j < 3; ++j) {
-            int r = 0, c = 0;
-            const int env = blockIdx.x + j * G;
-            if (env < N) update_loc_fixed<true>(p, env, action, ctrl, loc, r, c);
-            s_loc[j][0] = r; s_loc[j][1] = c;
-        }
-    }
+    // fov_loc of iterations [it0, it0 + 32) of this CTA, one per lane (called by A warp 0)
+    auto loc_batch = [&](int it0) {
+        const int j = it0 + (tid & 31);
+        const long long env = (long long)blockIdx.x + (long long)j * G;
+        int r = 0, c = 0;
+        if (env < N) update_loc_fixed<true>(p, (int)env, action, ctrl, loc, r, c);
+        s_loc[j & (LOC_RING - 1)][0] = r;
+        s_loc[j & (LOC_RING - 1)][1] = c;
+    };
+    if (tid >= NBT && tid < NBT + 32) loc_batch(0);
     __syncthreads();
 
-    if (tid >= NBW * 32) {
+    if (tid >= NBT) {
         // ================================================================== A warps
-        const int at = tid - NBW * 32;
+        const int at = tid - NBT;
         const bool a_active = at < NA;
-        const int a_rows = K * f_h;
-        auto prefetch = [&](int env, int slot_loc, int hh, int b) {
-            const int lr = s_loc[slot_loc][0], lc = s_loc[slot_loc][1];
-            float *sq = bufs + b * buf_words;
-            uint32_t *fv = reinterpret_cast<uint32_t *>(sq + K * PP);
-            const size_t slot0 = (size_t)env * K;
-            for (int c = at; c < K * (PP / 4); c += NAW * 32) {  // cached squeeze, logical frame order
-                const int k = c / (PP / 4), i = c - k * (PP / 4);
-                int slot = hh + 1 + k;
-                slot -= slot >= K ? K : 0;
-                cp_async16(sq + k * PP + 4 * i, pcache + (slot0 + slot) * PP + 4 * i);
-            }
-            const int wq0 = lc >> 2, nw = ((lc + p.f_w - 1) >> 2) - wq0 + 1;
-            for (int r = at; r < a_rows; r += NAW * 32) {  // ring words under the fovea, one row per pass
-                const int k = r / f_h, yy = r - k * f_h;
-                int slot = hh + 1 + k;
-                slot -= slot >= K ? K : 0;
-                const uint32_t *src = ring_w + (slot0 + slot) * PLANE_W + (uint32_t)(lr + yy) * Q + wq0;
-                uint32_t *dst = fv + r * nw_max;
-                for (int w = 0; w < nw; ++w) cp_async4(dst + w, src + w);
-            }
-        };
-        auto a_sync = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(NAW * 32) : "memory"); };
         // W-expand squeezed row `at` of the env in buffer b into T[tb]
         auto expand_w = [&](int b, int tb) {
             if (!a_active) return;
@@ -1210,36 +1210,15 @@ __global__ void __launch_bounds__((((StdGeom::Q * StdGeom::SEG * K + 31) / 32) +
                 t4[x4] = make_float4(o[0], o[1], o[2], o[3]);
             }
         };
-
+        __syncthreads();  // S2: the B warps have env e's (and e+G's) squeeze in shared memory
         int e = blockIdx.x;
-        int hh1 = 0, hh2 = 0;
-        if (e < N) prefetch(e, 0, head[e], 0);
-        cp_async_commit();
-        if (e + G < N) prefetch(e + G, 1, head[e + G], 1);
-        cp_async_commit();
-        if (e + 2 * G < N) hh2 = head[e + 2 * G];
-        cp_async_wait<1>();
-        a_sync();
         expand_w(0, 0);
-        __syncthreads();  // T[0], fovea(e) visible to the B warps
+        __syncthreads();  // S3: T[0] visible to the B warps
         for (int it = 0; e < N; e += G, ++it) {
-            const int e2 = e + 2 * G;
-            if (e2 < N) prefetch(e2, (it + 2) & 3, hh2, (it + 2) % 3);
-            cp_async_commit();
-            if (at == 0) {  // fov_loc of env e + 3G
-                int r = 0, c = 0;
-                if (e + 3 * G < N) update_loc_fixed<true>(p, e + 3 * G, action, ctrl, loc, r, c);
-                s_loc[(it + 3) & 3][0] = r; s_loc[(it + 3) & 3][1] = c;
-            }
-            hh1 = hh2;
-            hh2 = 0;
-            if (e + 3 * G < N) hh2 = head[e + 3 * G];
-            cp_async_wait<1>();  // env e+G has landed (this thread's copies); a_sync: everyone's
-            a_sync();
-            if (e + G < N) expand_w((it + 1) % 3, (it + 1) & 1);
+            if ((it & 31) == 0 && at < 32) loc_batch(it + 32);
+            if (e + G < N) expand_w((it + 1) % NBUF, (it + 1) & 1);
             __syncthreads();
         }
-        (void)hh1;
         return;
     }
 
@@ -1252,24 +1231,80 @@ __global__ void __launch_bounds__((((StdGeom::Q * StdGeom::SEG * K + 31) / 32) +
     const int off_t0 = (row_first < 0 ? 0 : row_first) * S + 4 * q;             // t = 0
     const int off_mid = row_first * S + 4 * q;                                     // t = 1..5 at + t * S
     const int off_t6 = (row_first + 6 > P - 1 ? P - 1 : row_first + 6) * S + 4 * q;  // t = 6
-    float hw[24];
-    {
-        const float4 *h4 = reinterpret_cast<const float4 *>(s_hw + g * 24);
-#pragma unroll
-        for (int i = 0; i < 6; ++i) {
-            const float4 v = h4[i];
-            hw[4 * i] = v.x; hw[4 * i + 1] = v.y; hw[4 * i + 2] = v.z; hw[4 * i + 3] = v.w;
-        }
-    }
+    const float4 *h4 = reinterpret_cast<const float4 *>(s_hw + g * 24);  // H weights of this segment's rows
     uint32_t *out_w = reinterpret_cast<uint32_t *>(out) + (size_t)k * PLANE_W + (uint32_t)(g * R) * Q + q;
 
-    __syncthreads();  // pairs with the A warps' prologue barrier: T[0] and the first fovea tile are ready
+    // ---- this thread's share of the prefetch (loop-invariant descriptors)
+    // packed as k | wc << 4 | offset << 12 (k = 15: nothing to do)
+    constexpr int NCH = (K * (PP / 4) + NBT - 1) / NBT;  // 16-byte chunks of the cached squeeze
+    int ch_d[NCH];
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) {
+        const int c = tid + j * NBT, kk = c / (PP / 4);
+        ch_d[j] = c < K * (PP / 4) ? (kk | (4 * (c - kk * (PP / 4))) << 12) : 15;
+    }
+    constexpr int NFW = 4;                               // staged fovea words w = tid + j * NBT
+    int fw_d[NFW];
+    const int per_k = f_h * nw_max;
+#pragma unroll
+    for (int j = 0; j < NFW; ++j) {
+        const int w = tid + j * NBT;
+        const int kk = w / per_k, rem = w - kk * per_k, yy = rem / nw_max, wc = rem - yy * nw_max;
+        fw_d[j] = w < fov_n ? (kk | wc << 4 | (yy * Q + wc) << 12) : 15;
+    }
+    auto prefetch = [&](int env, int it_env, int b) {
+        const int lr = s_loc[it_env & (LOC_RING - 1)][0], lc = s_loc[it_env & (LOC_RING - 1)][1];
+        const int hh = head[env];
+        float *sq = bufs + b * buf_words;
+        uint32_t *fv = reinterpret_cast<uint32_t *>(sq + K * PP);
+        const float *pc_env = pcache + (size_t)env * (K * PP);
+        const int wq0 = lc >> 2, nw = ((lc + p.f_w - 1) >> 2) - wq0 + 1;
+        const uint32_t *ring_env = ring_w + (size_t)env * (K * PLANE_W) + lr * Q + wq0;
+#pragma unroll
+        for (int j = 0; j < NCH; ++j) {  // cached squeeze, logical frame order
+            const int d = ch_d[j];
+            if ((d & 15) == 15) continue;
+            int slot = hh + 1 + (d & 15);
+            slot -= slot >= K ? K : 0;
+            cp_async16(sq + 4 * (tid + j * NBT), pc_env + slot * PP + (d >> 12));
+        }
+#pragma unroll
+        for (int j = 0; j < NFW; ++j) {  // ring words under the fovea
+            const int d = fw_d[j];
+            if ((d & 15) == 15 || ((d >> 4) & 255) >= nw) continue;
+            int slot = hh + 1 + (d & 15);
+            slot -= slot >= K ? K : 0;
+            cp_async4(fv + tid + j * NBT, ring_env + slot * PLANE_W + (d >> 12));
+        }
+        for (int w = tid + NFW * NBT; w < fov_n; w += NBT) {  // very large foveas only
+            const int kk = w / per_k, rem = w - kk * per_k, yy = rem / nw_max, wc = rem - yy * nw_max;
+            if (wc >= nw) continue;
+            int slot = hh + 1 + kk;
+            slot -= slot >= K ? K : 0;
+            cp_async4(fv + w, ring_env + slot * PLANE_W + yy * Q + wc);
+        }
+    };
+
+    {
+        const int e0 = blockIdx.x;
+        if (e0 < N) prefetch(e0, 0, 0);
+        cp_async_commit();
+        if (e0 + G < N) prefetch(e0 + G, 1, 1);
+        cp_async_commit();
+        if ((long long)e0 + 2LL * G < N) prefetch(e0 + 2 * G, 2, 2);
+        cp_async_commit();
+        cp_async_wait<1>();
+    }
+    __syncthreads();  // S2
+    __syncthreads();  // S3: T[0] is ready
     int it = 0;
     for (int e = blockIdx.x; e < N; e += G, ++it) {
+        if ((long long)e + 3LL * G < N) prefetch(e + 3 * G, it + 3, (it + 3) % NBUF);
+        cp_async_commit();
         if (b_active) {
-            const int lr = s_loc[it & 3][0], lc = s_loc[it & 3][1];
+            const int lr = s_loc[it & (LOC_RING - 1)][0], lc = s_loc[it & (LOC_RING - 1)][1];
             const float *tk = s_T + (it & 1) * T_FLOATS + k * (P * S);
-            const uint32_t *fvb = reinterpret_cast<const uint32_t *>(bufs + (it % 3) * buf_words + K * PP);
+            const uint32_t *fvb = reinterpret_cast<const uint32_t *>(bufs + (it % NBUF) * buf_words + K * PP);
             const uint32_t fov_mask = word_mask(4 * q, lc, lc + p.f_w);
             // rows r of this segment with r_lo <= r < r_lo + f_h meet the fovea: one bit per row
             const int r_lo = lr - g * R;
@@ -1285,6 +1320,7 @@ __global__ void __launch_bounds__((((StdGeom::Q * StdGeom::SEG * K + 31) / 32) +
                 b0 = b.x; b1 = b.y;
             }
             int t_have = 0;
+            float4 hw4 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 const int t = Gm::src(r) + 1;  // compile time: 0,0,1,1,1,1,2,...
@@ -1296,7 +1332,9 @@ __global__ void __launch_bounds__((((StdGeom::Q * StdGeom::SEG * K + 31) / 32) +
                     t_have = t;
                 }
                 if (r == 0 || Gm::src(r) != Gm::src(r - 1)) { d0 = fsub2(a0, b0); d1 = fsub2(a1, b1); }
-                const uint64_t w2 = pack2(hw[r], hw[r]);
+                if ((r & 3) == 0) hw4 = h4[r >> 2];
+                const float hwr = (r & 3) == 0 ? hw4.x : ((r & 3) == 1 ? hw4.y : ((r & 3) == 2 ? hw4.z : hw4.w));
+                const uint64_t w2 = pack2(hwr, hwr);
                 uint32_t u0, u1, u2, u3;
                 unpack2(ffma2(w2, d0, b0), u0, u1);
                 unpack2(ffma2(w2, d1, b1), u2, u3);
@@ -1306,6 +1344,7 @@ __global__ void __launch_bounds__((((StdGeom::Q * StdGeom::SEG * K + 31) / 32) +
                 o[r * Q] = word;
             }
         }
+        cp_async_wait<1>();  // this thread's copies for env e+2G have landed; the barrier publishes everyone's
         __syncthreads();
     }
 }
@@ -1545,25 +1584,23 @@ cudaError_t launch_observe_peripheral(const DevPlan &p, const ExpandStd *ew, con
     if (pcache && ew && ew->ok && (p.K == 4 || p.K == 3) && !g_disable_std) {
         const int nw_max = (p.f_w + 3) / 4 + 1;
         const size_t fov_words = ((size_t)p.K * p.f_h * nw_max + 3) & ~size_t(3);
-        const size_t fs = 4 * (2 * (size_t)p.K * 20 * 84 + 3 * ((size_t)p.K * 400 + fov_words) + 96);
-        int dev = 0, sms = 148, occ = 1;
+        const size_t fs = 4 * (2 * (size_t)p.K * 20 * 84 + 4 * ((size_t)p.K * 400 + fov_words) + 96);
+        int dev = 0, sms = 148, occ = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-#define AGYM_LAUNCH_STD(KK, NW)                                                                                    \
-    {                                                                                                              \
+#define AGYM_LAUNCH_STD(KK)                                                                                        \
+    if (fs <= 220 * 1024) {                                                                                        \
         const int threads = (((21 * 4 * KK + 31) / 32) + ((20 * KK + 31) / 32)) * 32;                              \
-        if ((e = set_smem(k_observe_peripheral_std<KK, NW>, fs)) != cudaSuccess) return e;                         \
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_observe_peripheral_std<KK, NW>, threads, fs);        \
+        if ((e = set_smem(k_observe_peripheral_std<KK>, fs)) != cudaSuccess) return e;                             \
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_observe_peripheral_std<KK>, threads, fs);            \
         if (occ >= 1) {                                                                                            \
-            k_observe_peripheral_std<KK, NW><<<std::min(p.N, sms * occ), threads, fs, st>>>(                       \
-                p, *ew, ring, head, pcache, action, ctrl, loc, out);                                               \
+            k_observe_peripheral_std<KK><<<std::min(p.N, sms * occ), threads, fs, st>>>(p, *ew, ring, head, pcache, \
+                                                                                       action, ctrl, loc, out);    \
             return cudaGetLastError();                                                                             \
         }                                                                                                          \
     }
-        if (p.K == 4 && nw_max == 9) AGYM_LAUNCH_STD(4, 9)
-        else if (p.K == 4) AGYM_LAUNCH_STD(4, 0)
-        else if (nw_max == 9) AGYM_LAUNCH_STD(3, 9)
-        else AGYM_LAUNCH_STD(3, 0)
+        if (p.K == 4) AGYM_LAUNCH_STD(4)
+        else AGYM_LAUNCH_STD(3)
 #undef AGYM_LAUNCH_STD
     }
     if (pcache && p.fast_expand && quads <= 64 && (p.p_h * p.p_w) % 4 == 0) {
