@@ -914,6 +914,12 @@ __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
 __device__ __forceinline__ void cp_async4(void *smem_dst, const void *gmem_src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src));
 }
+__device__ __forceinline__ void cp_async16_s(uint32_t smem_addr, const void *gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async4_s(uint32_t smem_addr, const void *gmem_src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_addr), "l"(gmem_src));
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
@@ -1141,7 +1147,7 @@ struct StdGeom {
     __host__ __device__ static constexpr int src(int i) { return (40 * i - 64 + 168 * 4) / 168 - 4; }
 };
 
-template <int K>
+template <int K, int NW>  // NW: words per staged fovea row, (f_w + 3) / 4 + 1, when baked in; 0 = from the plan
 __global__ void __launch_bounds__((((StdGeom::Q * StdGeom::SEG * K + 31) / 32) + ((StdGeom::P * K + 31) / 32)) * 32, 2)
     k_observe_peripheral_std(const __grid_constant__ DevPlan p, const __grid_constant__ ExpandStd ew,
                              const uint8_t *__restrict__ ring, const int32_t *__restrict__ head,
@@ -1158,7 +1164,7 @@ __global__ void __launch_bounds__((((StdGeom::Q * StdGeom::SEG * K + 31) / 32) +
     __shared__ int s_loc[LOC_RING][2];
     const int tid = threadIdx.x;
     const int N = p.N, f_h = p.f_h, G = gridDim.x;
-    const int nw_max = (p.f_w + 3) / 4 + 1;
+    const int nw_max = NW ? NW : (p.f_w + 3) / 4 + 1;
     const int fov_n = K * f_h * nw_max;                              // staged fovea words per env
     const int buf_words = K * PP + ((fov_n + 3) & ~3);
     float *s_T = reinterpret_cast<float *>(smem);                    // [2][K][P][S], biased
@@ -1173,9 +1179,10 @@ __global__ void __launch_bounds__((((StdGeom::Q * StdGeom::SEG * K + 31) / 32) +
     // fov_loc of iterations [it0, it0 + 32) of this CTA, one per lane (called by A warp 0)
     auto loc_batch = [&](int it0) {
         const int j = it0 + (tid & 31);
-        const long long env = (long long)blockIdx.x + (long long)j * G;
+        // j * G cannot overflow: a CTA runs at most N / G + 1 iterations and batches reach 64 past that
+        const int env = j <= N / G + 1 ? (int)blockIdx.x + j * G : N;
         int r = 0, c = 0;
-        if (env < N) update_loc_fixed<true>(p, (int)env, action, ctrl, loc, r, c);
+        if (env < N) update_loc_fixed<true>(p, env, action, ctrl, loc, r, c);
         s_loc[j & (LOC_RING - 1)][0] = r;
         s_loc[j & (LOC_RING - 1)][1] = c;
     };
@@ -1235,72 +1242,85 @@ __global__ void __launch_bounds__((((StdGeom::Q * StdGeom::SEG * K + 31) / 32) +
     uint32_t *out_w = reinterpret_cast<uint32_t *>(out) + (size_t)k * PLANE_W + (uint32_t)(g * R) * Q + q;
 
     // ---- this thread's share of the prefetch (loop-invariant descriptors)
-    // packed as k | wc << 4 | offset << 12 (k = 15: nothing to do)
-    constexpr int NCH = (K * (PP / 4) + NBT - 1) / NBT;  // 16-byte chunks of the cached squeeze
-    int ch_d[NCH];
+    // cached squeeze: 16-byte chunks c = tid + j * NBT -> frame c / 100, float offset 4 * (c % 100)
+    constexpr int NCH = (K * (PP / 4) + NBT - 1) / NBT;
+    int ch_d[NCH];  // frame | float offset << 4; -1 = none
 #pragma unroll
     for (int j = 0; j < NCH; ++j) {
         const int c = tid + j * NBT, kk = c / (PP / 4);
-        ch_d[j] = c < K * (PP / 4) ? (kk | (4 * (c - kk * (PP / 4))) << 12) : 15;
+        ch_d[j] = c < K * (PP / 4) ? (kk | (4 * (c - kk * (PP / 4))) << 4) : -1;
     }
-    constexpr int NFW = 4;                               // staged fovea words w = tid + j * NBT
-    int fw_d[NFW];
-    const int per_k = f_h * nw_max;
+    // ring words under the fovea: task t = tid + j * NBT -> staged row t / 2 = (k, yy), half t % 2 of its nw_max words
+    constexpr int NFT = 2;
+    const int f_rows = K * f_h, half0 = (nw_max + 1) >> 1;
+    int ft_d[NFT], ft_w[NFT];  // frame | first word << 4 | yy << 12 (-1 = none); staged word index
 #pragma unroll
-    for (int j = 0; j < NFW; ++j) {
-        const int w = tid + j * NBT;
-        const int kk = w / per_k, rem = w - kk * per_k, yy = rem / nw_max, wc = rem - yy * nw_max;
-        fw_d[j] = w < fov_n ? (kk | wc << 4 | (yy * Q + wc) << 12) : 15;
+    for (int j = 0; j < NFT; ++j) {
+        const int t = tid + j * NBT, r = t >> 1, kk = r / f_h, yy = r - kk * f_h, w0 = (t & 1) ? half0 : 0;
+        ft_d[j] = r < f_rows ? (kk | w0 << 4 | yy << 12) : -1;
+        ft_w[j] = r * nw_max + w0;
     }
-    auto prefetch = [&](int env, int it_env, int b) {
+    const uint32_t bufs_s = smem_u32(bufs);
+    auto prefetch = [&](int env, int it_env, int b, int hh) {
         const int lr = s_loc[it_env & (LOC_RING - 1)][0], lc = s_loc[it_env & (LOC_RING - 1)][1];
-        const int hh = head[env];
-        float *sq = bufs + b * buf_words;
-        uint32_t *fv = reinterpret_cast<uint32_t *>(sq + K * PP);
+        const uint32_t sq_s = bufs_s + (uint32_t)(b * buf_words) * 4u + (uint32_t)tid * 16u;  // this thread's first chunk
+        const uint32_t fv_s = bufs_s + (uint32_t)(b * buf_words + K * PP) * 4u;
         const float *pc_env = pcache + (size_t)env * (K * PP);
         const int wq0 = lc >> 2, nw = ((lc + p.f_w - 1) >> 2) - wq0 + 1;
         const uint32_t *ring_env = ring_w + (size_t)env * (K * PLANE_W) + lr * Q + wq0;
 #pragma unroll
         for (int j = 0; j < NCH; ++j) {  // cached squeeze, logical frame order
             const int d = ch_d[j];
-            if ((d & 15) == 15) continue;
+            if (d < 0) continue;
             int slot = hh + 1 + (d & 15);
             slot -= slot >= K ? K : 0;
-            cp_async16(sq + 4 * (tid + j * NBT), pc_env + slot * PP + (d >> 12));
+            cp_async16_s(sq_s + (uint32_t)(j * NBT) * 16u, pc_env + slot * PP + (d >> 4));
         }
-#pragma unroll
-        for (int j = 0; j < NFW; ++j) {  // ring words under the fovea
-            const int d = fw_d[j];
-            if ((d & 15) == 15 || ((d >> 4) & 255) >= nw) continue;
-            int slot = hh + 1 + (d & 15);
-            slot -= slot >= K ? K : 0;
-            cp_async4(fv + tid + j * NBT, ring_env + slot * PLANE_W + (d >> 12));
-        }
-        for (int w = tid + NFW * NBT; w < fov_n; w += NBT) {  // very large foveas only
-            const int kk = w / per_k, rem = w - kk * per_k, yy = rem / nw_max, wc = rem - yy * nw_max;
-            if (wc >= nw) continue;
+        auto half_row = [&](int kk, int w0, int yy, int widx) {
             int slot = hh + 1 + kk;
             slot -= slot >= K ? K : 0;
-            cp_async4(fv + w, ring_env + slot * PLANE_W + yy * Q + wc);
+            const uint32_t *src = ring_env + slot * PLANE_W + yy * Q + w0;
+            const uint32_t dst = fv_s + (uint32_t)widx * 4u;
+            const int n = nw - w0;  // words of this half that exist: min(n, half)
+            if (NW) {
+#pragma unroll
+                for (int w = 0; w < (NW + 1) / 2; ++w)
+                    if (w < n && w0 + w < (w0 ? NW : (NW + 1) / 2)) cp_async4_s(dst + 4u * w, src + w);
+            } else {
+                const int lim = w0 ? nw_max - half0 : half0;
+                for (int w = 0; w < lim && w < n; ++w) cp_async4_s(dst + 4u * w, src + w);
+            }
+        };
+#pragma unroll
+        for (int j = 0; j < NFT; ++j) {
+            const int d = ft_d[j];
+            if (d >= 0) half_row(d & 15, (d >> 4) & 255, d >> 12, ft_w[j]);
+        }
+        for (int t = tid + NFT * NBT; t < 2 * f_rows; t += NBT) {  // very tall foveas only
+            const int r = t >> 1, kk = r / f_h, yy = r - kk * f_h, w0 = (t & 1) ? half0 : 0;
+            half_row(kk, w0, yy, r * nw_max + w0);
         }
     };
 
+    int hh_next = 0;  // head of the env the next iteration prefetches, loaded one iteration ahead
     {
         const int e0 = blockIdx.x;
-        if (e0 < N) prefetch(e0, 0, 0);
+        if (e0 < N) prefetch(e0, 0, 0, head[e0]);
         cp_async_commit();
-        if (e0 + G < N) prefetch(e0 + G, 1, 1);
+        if (e0 + G < N) prefetch(e0 + G, 1, 1, head[e0 + G]);
         cp_async_commit();
-        if ((long long)e0 + 2LL * G < N) prefetch(e0 + 2 * G, 2, 2);
+        if (e0 + 2 * G < N) prefetch(e0 + 2 * G, 2, 2, head[e0 + 2 * G]);
         cp_async_commit();
+        if (e0 + 3 * G < N) hh_next = head[e0 + 3 * G];
         cp_async_wait<1>();
     }
     __syncthreads();  // S2
     __syncthreads();  // S3: T[0] is ready
     int it = 0;
     for (int e = blockIdx.x; e < N; e += G, ++it) {
-        if ((long long)e + 3LL * G < N) prefetch(e + 3 * G, it + 3, (it + 3) % NBUF);
+        if (e + 3 * G < N) prefetch(e + 3 * G, it + 3, (it + 3) % NBUF, hh_next);
         cp_async_commit();
+        if (e + 4 * G < N) hh_next = head[e + 4 * G];
         if (b_active) {
             const int lr = s_loc[it & (LOC_RING - 1)][0], lc = s_loc[it & (LOC_RING - 1)][1];
             const float *tk = s_T + (it & 1) * T_FLOATS + k * (P * S);
@@ -1581,26 +1601,30 @@ cudaError_t launch_observe_peripheral(const DevPlan &p, const ExpandStd *ew, con
     const size_t smem = a16(p.plane) + sizeof(float) * ((size_t)p.S_h * p.p_w + (size_t)p.p_h * p.p_w + (size_t)p.p_h * p.S_w);
     cudaError_t e;
     const int quads = p.S_w / 4;
-    if (pcache && ew && ew->ok && (p.K == 4 || p.K == 3) && !g_disable_std) {
+    if (pcache && ew && ew->ok && (p.K == 4 || p.K == 3) && !g_disable_std && p.N < (1 << 30)) {
         const int nw_max = (p.f_w + 3) / 4 + 1;
         const size_t fov_words = ((size_t)p.K * p.f_h * nw_max + 3) & ~size_t(3);
         const size_t fs = 4 * (2 * (size_t)p.K * 20 * 84 + 4 * ((size_t)p.K * 400 + fov_words) + 96);
         int dev = 0, sms = 148, occ = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-#define AGYM_LAUNCH_STD(KK)                                                                                        \
+#define AGYM_LAUNCH_STD(KK, NW)                                                                                    \
+    {                                                                                                              \
     if (fs <= 220 * 1024) {                                                                                        \
         const int threads = (((21 * 4 * KK + 31) / 32) + ((20 * KK + 31) / 32)) * 32;                              \
-        if ((e = set_smem(k_observe_peripheral_std<KK>, fs)) != cudaSuccess) return e;                             \
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_observe_peripheral_std<KK>, threads, fs);            \
+        if ((e = set_smem(k_observe_peripheral_std<KK, NW>, fs)) != cudaSuccess) return e;                         \
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_observe_peripheral_std<KK, NW>, threads, fs);        \
         if (occ >= 1) {                                                                                            \
-            k_observe_peripheral_std<KK><<<std::min(p.N, sms * occ), threads, fs, st>>>(p, *ew, ring, head, pcache, \
-                                                                                       action, ctrl, loc, out);    \
+            k_observe_peripheral_std<KK, NW><<<std::min(p.N, sms * occ), threads, fs, st>>>(                       \
+                p, *ew, ring, head, pcache, action, ctrl, loc, out);                                               \
             return cudaGetLastError();                                                                             \
         }                                                                                                          \
+    }                                                                                                              \
     }
-        if (p.K == 4) AGYM_LAUNCH_STD(4)
-        else AGYM_LAUNCH_STD(3)
+        if (p.K == 4 && nw_max == 9) AGYM_LAUNCH_STD(4, 9)
+        else if (p.K == 4) AGYM_LAUNCH_STD(4, 0)
+        else if (nw_max == 9) AGYM_LAUNCH_STD(3, 9)
+        else AGYM_LAUNCH_STD(3, 0)
 #undef AGYM_LAUNCH_STD
     }
     if (pcache && p.fast_expand && quads <= 64 && (p.p_h * p.p_w) % 4 == 0) {
