@@ -223,8 +223,12 @@ int agym_plan_create(const agym_config *cfg, agym_plan **out_plan) {
                 if (raw < 0) ok = ok && ww[i] == 1.f && hw[i] == 1.f;       // out = t[0]
                 if (raw > 18) ok = ok && ww[i] == 0.f && hw[i] == 0.f;      // out = t[19]
             }
+            // H weights repeat every 21 rows bit for bit, except at the clamped border rows (0, 1, 82, 83)
+            // where both taps read the same squeezed row and the weight is irrelevant
+            for (int i = 2; ok && i < 82; ++i) ok = std::memcmp(&hw[i], &hw[21 + (i % 21)], sizeof(float)) == 0 || (21 + i % 21 >= 82);
             if (ok) {
                 for (int i = 0; i < 84; ++i) { es.w0[i] = ww[i]; es.w1[i] = ww1[i]; }
+                for (int r = 0; r < 21; ++r) es.hw[r] = hw[21 + r];
             }
             es.ok = ok;
         }

@@ -1169,13 +1169,8 @@ __global__ void __launch_bounds__((((StdGeom::Q * StdGeom::SEG * K + 31) / 32) +
     const int buf_words = K * PP + ((fov_n + 3) & ~3);
     float *s_T = reinterpret_cast<float *>(smem);                    // [2][K][P][S], biased
     float *bufs = s_T + 2 * T_FLOATS;                                // [NBUF]{ sq [K][P][P] | fov [K][f_h][nw_max] }
-    float *s_hw = bufs + NBUF * buf_words;                           // [SEG][24] H weights (w0) per segment row
     const uint32_t *ring_w = reinterpret_cast<const uint32_t *>(ring);
 
-    for (int i = tid; i < Gm::SEG * 24; i += blockDim.x) {
-        const int g = i / 24, r = i - g * 24;
-        s_hw[i] = r < R ? __ldg(p.exh_w0 + g * R + r) : 0.f;
-    }
     // fov_loc of iterations [it0, it0 + 32) of this CTA, one per lane (called by A warp 0)
     auto loc_batch = [&](int it0) {
         const int j = it0 + (tid & 31);
@@ -1238,7 +1233,6 @@ __global__ void __launch_bounds__((((StdGeom::Q * StdGeom::SEG * K + 31) / 32) +
     const int off_t0 = (row_first < 0 ? 0 : row_first) * S + 4 * q;             // t = 0
     const int off_mid = row_first * S + 4 * q;                                     // t = 1..5 at + t * S
     const int off_t6 = (row_first + 6 > P - 1 ? P - 1 : row_first + 6) * S + 4 * q;  // t = 6
-    const float4 *h4 = reinterpret_cast<const float4 *>(s_hw + g * 24);  // H weights of this segment's rows
     uint32_t *out_w = reinterpret_cast<uint32_t *>(out) + (size_t)k * PLANE_W + (uint32_t)(g * R) * Q + q;
 
     // ---- this thread's share of the prefetch (loop-invariant descriptors)
@@ -1340,7 +1334,6 @@ __global__ void __launch_bounds__((((StdGeom::Q * StdGeom::SEG * K + 31) / 32) +
                 b0 = b.x; b1 = b.y;
             }
             int t_have = 0;
-            float4 hw4 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 const int t = Gm::src(r) + 1;  // compile time: 0,0,1,1,1,1,2,...
@@ -1352,9 +1345,9 @@ __global__ void __launch_bounds__((((StdGeom::Q * StdGeom::SEG * K + 31) / 32) +
                     t_have = t;
                 }
                 if (r == 0 || Gm::src(r) != Gm::src(r - 1)) { d0 = fsub2(a0, b0); d1 = fsub2(a1, b1); }
-                if ((r & 3) == 0) hw4 = h4[r >> 2];
-                const float hwr = (r & 3) == 0 ? hw4.x : ((r & 3) == 1 ? hw4.y : ((r & 3) == 2 ? hw4.z : hw4.w));
-                const uint64_t w2 = pack2(hwr, hwr);
+                // H weight of row r: the same for every segment (the plan checked it); at the clamped
+                // border rows a == b, so the weight does not matter there
+                const uint64_t w2 = pack2(ew.hw[r], ew.hw[r]);
                 uint32_t u0, u1, u2, u3;
                 unpack2(ffma2(w2, d0, b0), u0, u1);
                 unpack2(ffma2(w2, d1, b1), u2, u3);
@@ -1604,7 +1597,7 @@ cudaError_t launch_observe_peripheral(const DevPlan &p, const ExpandStd *ew, con
     if (pcache && ew && ew->ok && (p.K == 4 || p.K == 3) && !g_disable_std && p.N < (1 << 30)) {
         const int nw_max = (p.f_w + 3) / 4 + 1;
         const size_t fov_words = ((size_t)p.K * p.f_h * nw_max + 3) & ~size_t(3);
-        const size_t fs = 4 * (2 * (size_t)p.K * 20 * 84 + 4 * ((size_t)p.K * 400 + fov_words) + 96);
+        const size_t fs = 4 * (2 * (size_t)p.K * 20 * 84 + 4 * ((size_t)p.K * 400 + fov_words));
         int dev = 0, sms = 148, occ = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

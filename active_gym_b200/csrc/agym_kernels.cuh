@@ -58,8 +58,9 @@ struct DevPlan {
 // to k_observe_peripheral_std by value so that they sit in the constant bank.  ok = the plan's
 // tables follow the compile-time tap pattern of that kernel.
 struct ExpandStd {
-    float w0[84];
+    float w0[84];   // W pass: out[x] = w0[x] * t[i0] + w1[x] * t[i0 + 1]
     float w1[84];
+    float hw[21];   // H pass: weight of the upper row for row r of any 21-row segment
     int32_t ok;
 };
 
