@@ -169,7 +169,8 @@ int agym_plan_create(const agym_config *cfg, agym_plan **out_plan) {
     if (fast_ingest) { o_pair = pool.add_i(pair_tab); o_ybs = pool.add_i(ybs_tab); }
     // squeeze along W straight from u8 rows: a 16-byte window per output column
     bool fast_squeeze = c.periph_h > 0;
-    size_t o_sqofs = 0, o_sqw = 0;
+    size_t o_sqofs = 0, o_sqw = 0, o_sqq = 0;
+    bool squeeze_q = false;
     int sq_taps4 = 0;
     if (fast_squeeze) {
         const AaAxis ax = build_aa_axis(c.obs_w, c.periph_w);
@@ -183,6 +184,26 @@ int agym_plan_create(const agym_config *cfg, agym_plan **out_plan) {
             for (int j = 0; j < ax.taps; ++j) wts[static_cast<size_t>(i) * sq_taps4 + j] = ax.w[static_cast<size_t>(i) * ax.taps + j];
         }
         if (fast_squeeze) { o_sqofs = pool.add_i(ofs); o_sqw = pool.add_f(wts); }
+        // fixed-point form: q_j = round(w_j * 2^17), largest weight adjusted so that the sum is 2^17 exactly
+        squeeze_q = fast_squeeze;
+        std::vector<int32_t> qtab(static_cast<size_t>(ax.n_out) * 8, 0);
+        for (int i = 0; squeeze_q && i < ax.n_out; ++i) {
+            std::vector<long> q(ax.taps);
+            long sum = 0;
+            int jmax = 0;
+            for (int j = 0; j < ax.taps; ++j) {
+                q[j] = std::lround(static_cast<double>(ax.w[static_cast<size_t>(i) * ax.taps + j]) * 131072.0);
+                sum += q[j];
+                if (q[j] > q[jmax]) jmax = j;
+            }
+            q[jmax] += 131072 - sum;
+            for (int j = 0; j < ax.taps; ++j) {
+                if (q[j] < 0 || q[j] > 32767) squeeze_q = false;
+                const int t = (ax.xmin[i] & 3) + j;  // position inside the aligned 16-byte window
+                qtab[static_cast<size_t>(i) * 8 + t / 2] |= static_cast<int32_t>(static_cast<uint32_t>(q[j] & 0xffff) << (16 * (t & 1)));
+            }
+        }
+        if (squeeze_q) o_sqq = pool.add_i(qtab);
     }
     // expand p -> S as two-tap lerps (plain bilinear upsampling: antialiasing is inactive)
     bool fast_expand = c.periph_h > 0 && c.periph_h < c.obs_h && c.periph_w < c.obs_w && c.periph_h >= 2 && c.periph_w >= 2;
@@ -287,6 +308,8 @@ int agym_plan_create(const agym_config *cfg, agym_plan **out_plan) {
     if (fast_squeeze) {
         d.sqw_ofs = reinterpret_cast<const int2 *>(base + o_sqofs);
         d.sqw_w = reinterpret_cast<const float *>(base + o_sqw);
+        d.squeeze_q = squeeze_q;
+        if (squeeze_q) d.sqw_q = base + o_sqq;
     }
     d.fast_expand = fast_expand;
     if (fast_expand) {

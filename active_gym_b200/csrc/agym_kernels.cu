@@ -517,6 +517,9 @@ __global__ void __launch_bounds__(kIngestThreads, 3) k_ingest_atari_tma(const __
     int4 *s_row = reinterpret_cast<int4 *>(s_t1 + (pcache ? p.S_h * p.p_w : 0));  // [S_h] {ofs0, ofs1, b0<<16, b1<<16}
     int2 *s_span = reinterpret_cast<int2 *>(s_row + p.S_h);                       // [units] {first row, bytes}
     float *s_sqw = reinterpret_cast<float *>(s_span + ((units + 1) & ~1));        // [p_w][taps4], 16-byte aligned
+    uint32_t *s_sqq = reinterpret_cast<uint32_t *>(s_sqw + (pcache ? p.p_w * 16 : 0));  // [p_w][8] fixed-point W weights
+    float *s_sqh = reinterpret_cast<float *>(s_sqq + (pcache ? p.p_w * 8 : 0));         // [p_h][taps] H-pass weights
+    int32_t *s_sqx = reinterpret_cast<int32_t *>(s_sqh + (pcache ? p.p_h * p.sq_h.taps : 0));  // [p_h] first source row
     const size_t frame_bytes = (size_t)p.raw_h * raw_w;
 
     if (tid == 0) {
@@ -534,6 +537,11 @@ __global__ void __launch_bounds__(kIngestThreads, 3) k_ingest_atari_tma(const __
     }
     if (pcache && p.fast_squeeze)
         for (int i = tid; i < p.p_w * p.sqw_taps4; i += kIngestThreads) s_sqw[i] = __ldg(p.sqw_w + i);
+    if (pcache) {
+        for (int i = tid; i < p.p_w * 8; i += kIngestThreads) s_sqq[i] = p.squeeze_q ? __ldg(p.sqw_q + i) : 0u;
+        for (int i = tid; i < p.p_h * p.sq_h.taps; i += kIngestThreads) s_sqh[i] = __ldg(p.sq_h.w + i);
+        for (int i = tid; i < p.p_h; i += kIngestThreads) s_sqx[i] = __ldg(p.sq_h.xmin + i);
+    }
     __syncthreads();
 
     // unit `it` of this CTA: env = blockIdx.x + (it / units) * gridDim.x, part = it % units
@@ -577,6 +585,7 @@ __global__ void __launch_bounds__(kIngestThreads, 3) k_ingest_atari_tma(const __
     const int nq = p.sqw_taps4 >> 2;
     const int2 sq_o = sq_worker ? __ldg(p.sqw_ofs + sq_i) : make_int2(0, 0);
     const float4 *sqw4 = reinterpret_cast<const float4 *>(s_sqw + sq_i * p.sqw_taps4);
+    const uint4 *sqq4 = reinterpret_cast<const uint4 *>(s_sqq) + 2 * sq_i;  // fixed-point weights of this column
 
     int slot = 0, fl = 0;
     for (int it = 0, n = blockIdx.x, part = 0, st = 0, ph = 0; it < my_units; ++it) {
@@ -659,7 +668,24 @@ __global__ void __launch_bounds__(kIngestThreads, 3) k_ingest_atari_tma(const __
         uint4 *out4 = reinterpret_cast<uint4 *>(ring + ((size_t)n * K + slot) * p.plane);
         for (int i = tid; i < p.plane / 16; i += kThreads) out4[i] = reinterpret_cast<const uint4 *>(s_frame)[i];
         if (pcache) {  // uniform
-            if (sq_rows) {
+            if (sq_rows && p.squeeze_q) {
+                // W pass in 16-bit fixed point: 8 IDP.2A over the aligned 16-byte window, exact integer sum
+                if (sq_worker) {
+                    for (int y = sq_y0; y < p.S_h; y += sq_rows) {
+                        const uint32_t *src = reinterpret_cast<const uint32_t *>(s_frame + y * S_w + sq_o.x);
+                        const uint4 qa = sqq4[0], qb = sqq4[1];
+                        uint32_t acc = __dp2a_lo(qa.x, src[0], 0u);
+                        acc = __dp2a_hi(qa.y, src[0], acc);
+                        acc = __dp2a_lo(qa.z, src[1], acc);
+                        acc = __dp2a_hi(qa.w, src[1], acc);
+                        acc = __dp2a_lo(qb.x, src[2], acc);
+                        acc = __dp2a_hi(qb.y, src[2], acc);
+                        acc = __dp2a_lo(qb.z, src[3], acc);
+                        acc = __dp2a_hi(qb.w, src[3], acc);
+                        s_t1[y * p.p_w + sq_i] = (float)acc * (1.f / 131072.f);
+                    }
+                }
+            } else if (sq_rows) {
                 if (sq_worker) {
                     for (int y = sq_y0; y < p.S_h; y += sq_rows) {
                         const uint32_t *src = reinterpret_cast<const uint32_t *>(s_frame + y * S_w + sq_o.x);
@@ -685,7 +711,23 @@ __global__ void __launch_bounds__(kIngestThreads, 3) k_ingest_atari_tma(const __
                 resample_w<uint8_t>(s_frame, S_w, s_t1, p.p_w, p.S_h, p.sq_w, tid, kThreads);
             }
             consumer_sync();
-            resample_h<float>(s_t1, p.p_w, pcache + ((size_t)n * K + slot) * p.p_h * p.p_w, p.p_w, p.p_w, p.sq_h, tid, kThreads);
+            {   // H pass: out[i][j] = sum_t wh[i][t] * t1[xmin[i] + t][j], weights from shared memory
+                float *dst = pcache + ((size_t)n * K + slot) * p.p_h * p.p_w;
+                const int pw = p.p_w, taps = p.sq_h.taps, total = p.p_h * pw;
+                for (int o = tid; o < total; o += kThreads) {
+                    const int i = o / pw, j = o - i * pw;
+                    const float *w = s_sqh + i * taps;
+                    const float *t = s_t1 + s_sqx[i] * pw + j;
+                    float acc0 = 0.f, acc1 = 0.f;
+                    int tt = 0;
+                    for (; tt + 1 < taps; tt += 2) {
+                        acc0 = fmaf(w[tt], t[tt * pw], acc0);
+                        acc1 = fmaf(w[tt + 1], t[(tt + 1) * pw], acc1);
+                    }
+                    if (tt < taps) acc0 = fmaf(w[tt], t[tt * pw], acc0);
+                    dst[o] = acc0 + acc1;
+                }
+            }
         }
         consumer_sync();  // s_frame / s_t1 are reused by the next env
         }
@@ -1526,7 +1568,7 @@ cudaError_t launch_ingest_atari(const DevPlan &p, const uint8_t *fa, const uint8
         const int units = ui, span_rows = p.tma_span_rows[ui - 1];
         const size_t stage = a16(2 * ((size_t)span_rows * p.raw_w + 16));
         size_t fs = 2 * stage + a16(p.plane + 16) + 16 * (size_t)p.S_h + 8 * (size_t)((units + 1) & ~1);
-        if (pcache) fs += sizeof(float) * ((size_t)p.S_h * p.p_w + (size_t)p.p_w * 16);
+        if (pcache) fs += sizeof(float) * ((size_t)p.S_h * p.p_w + (size_t)p.p_w * 24 + (size_t)p.p_h * p.sq_h.taps + (size_t)p.p_h);
         int dev = 0, sms = 148, occ = 1;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

@@ -48,6 +48,10 @@ struct DevPlan {
     int32_t fast_squeeze, sqw_taps4;  // taps padded to a multiple of 4
     const int2 *sqw_ofs;    // [p_w] {aligned byte offset, 8 * (xmin & 3)}
     const float *sqw_w;     // [p_w][sqw_taps4]
+    // the same pass in 16-bit fixed point (weights * 2^17, summing to 2^17 exactly) for IDP.2A: per output
+    // column 8 words = 16 weights aligned to the 16-byte window at sqw_ofs.x (0 = geometry not eligible)
+    int32_t squeeze_q;
+    const uint32_t *sqw_q;  // [p_w][8]
     // expand p -> S as two taps: out = w0 * t[i0] + w1 * t[i0+1]  (w1 is given along W only)
     int32_t fast_expand;
     const int32_t *exw_i0, *exh_i0;   // [S_w], [S_h]
