@@ -137,6 +137,12 @@ class CpuReference:
         wall = time.perf_counter() - t0
         return self.procs * n_steps / wall, wall
 
+    def calibrate(self, target_s, probe=64):
+        """Env-steps per process that take about `target_s` seconds of wall time."""
+        self.run(probe)
+        rate, wall = self.run(probe)
+        return max(probe, int(probe * target_s / max(wall, 1e-6)))
+
     def close(self):
         for c in self.conns:
             c.send(None)
@@ -158,8 +164,9 @@ def run_reference_arm(a):
         return
     w = WORKLOADS[a.workload]
     procs = host_cores()
-    per_step = a.cpu_steps_per_proc
     ref = CpuReference(a.workload, procs)
+    # each bench step = a bounded sample of about --cpu-seconds / steps seconds on every host core
+    per_step = a.cpu_steps_per_proc or ref.calibrate(max(a.cpu_seconds / max(a.steps, 1), 0.5))
     for _ in range(max(a.warmup, 1)):
         ref.run(max(per_step // 4, 8))
     t_steps = [ref.run(per_step)[1] for _ in range(a.steps)]
@@ -354,12 +361,13 @@ def run_b200_arm(a):
         # before CUDA is initialised in this process (workers are forked)
         procs = host_cores()
         ref = CpuReference(a.workload, procs)
-        ref.run(max(a.cpu_steps_per_proc // 4, 8))
-        rate, wall = ref.run(a.cpu_steps_per_proc * 4)
+        n_cpu = a.cpu_steps_per_proc or ref.calibrate(a.cpu_seconds)
+        rate, wall = ref.run(n_cpu)
         ref.close()
         cpu = {"value": rate, "unit": UNIT, "cores": procs, "kind": "port",
-               "sample": f"{procs} single-env processes x {a.cpu_steps_per_proc * 4} env-steps of oracle/ref_port.py "
-                         f"(the reference's per-env cv2/numpy/torchvision path), {wall:.1f}s wall"}
+               "sample": f"{procs} single-env processes x {n_cpu} env-steps of oracle/ref_port.py "
+                         f"(the reference's per-env cv2/numpy/torchvision path), {wall:.1f}s wall = "
+                         f"{wall * procs:.0f} core-seconds"}
     import torch
     dist = None
     if world > 1:
@@ -457,7 +465,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="atari_peripheral", choices=sorted(WORKLOADS))
     ap.add_argument("--envs", type=int, default=None, help="envs per GPU (default: the BASELINE config's N)")
-    ap.add_argument("--cpu-steps-per-proc", type=int, default=150)
+    ap.add_argument("--cpu-steps-per-proc", type=int, default=0, help="env-steps per CPU process and sample (0 = calibrate from --cpu-seconds)")
+    ap.add_argument("--cpu-seconds", type=float, default=1.5, help="wall seconds of the bounded CPU sample (x host cores = CPU work)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     a = ap.parse_args()
