@@ -20,7 +20,7 @@ from .engine import LUMA_DMC, LUMA_RGB, ObservationPath
 class HostPipelinedEnv:
     def __init__(self, n_envs: int, frame_stack: int, obs_size, raw_shape, kind: str = "atari", wrapper: str = "fixed",
                  variant: str = "crop", fov_size=(30, 30), fov_init_loc=(0, 0), sensory_action_mode: str = "absolute",
-                 sensory_action_space=(-10.0, 10.0), peripheral_res=None, device=None, shards: int = 4):
+                 sensory_action_space=(-10.0, 10.0), peripheral_res=None, device=None, shards: int = 16):
         self.kind, self.wrapper, self.variant = kind, wrapper, variant
         self.n_envs = int(n_envs)
         self.device = torch.device(device if device is not None else "cuda")
@@ -52,7 +52,7 @@ class HostPipelinedEnv:
         self.d2h_bytes_per_step = int(self.h_obs.numel()) + self.n_envs * 8
 
     @classmethod
-    def from_workload(cls, w, n, device, shards=4, obs_size=(84, 84)):
+    def from_workload(cls, w, n, device, shards=16, obs_size=(84, 84)):
         return cls(n, w["K"], obs_size, w["raw"], kind=w["kind"], wrapper=w["wrapper"], variant=w["variant"],
                    fov_size=w["fov"], sensory_action_mode=w["mode"], peripheral_res=w["periph"], device=device, shards=shards)
 

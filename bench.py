@@ -319,7 +319,7 @@ def time_kernel(torch, fn, reps, warmup=3):
     return sum(ts) / len(ts), min(ts)
 
 
-def measure_e2e(torch, wl, steps, warmup, shards=4):
+def measure_e2e(torch, wl, steps, warmup, shards=32):
     """The same env step through the public batched-env API with HOST buffers: every step copies the
     step's raw frames + actions from pinned host memory to the GPU and the observations back to
     pinned host memory (all inside the timed region).  The batch is cut into `shards` env shards,
@@ -404,6 +404,29 @@ def run_b200_arm(a):
             avg, best = time_kernel(torch, call, reps)
             kern[kname] = {"ms": avg * 1e3, "ms_best": best * 1e3, "alg_bytes_per_obs": nb,
                            "achieved_gbs": nb * wl.n / avg / 1e9, "obs_per_s": wl.n / avg}
+    # end to end through the host-buffer API, on every rank at the same time (they share the host's
+    # memory system); time = max over ranks, envs = sum over ranks
+    e2e_all = None
+    if not a.no_e2e:
+        e_steps = max(a.steps // 2, 3)
+        err = None
+        try:
+            if dist is not None:
+                dist.barrier()
+            edt, h2d, d2h = measure_e2e(torch, wl, e_steps, 2)
+        except Exception as ex:  # never lose the line over the e2e leg
+            edt, h2d, d2h, err = float("inf"), 0, 0, repr(ex)[:200]
+        if dist is not None:
+            t = torch.tensor([edt if edt != float("inf") else 1e30], device=device, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            edt = float(t.item())
+        if err is None and edt < 1e29:
+            e2e_all = {"value": wl.n * world * e_steps / edt, "unit": UNIT, "h2d_bytes_per_step": h2d * world,
+                       "d2h_bytes_per_step": d2h * world, "n_gpus": world, "steps": e_steps,
+                       "note": "HostPipelinedEnv.step_host on every rank: pinned host frames+actions -> H2D -> "
+                               "ingest+observe -> D2H observations; host wall clock, max over ranks"}
+        else:
+            e2e_all = {"value": None, "unit": UNIT, "error": err or "a rank failed"}
     line = None
     if rank == 0:
         peaks = {}
@@ -425,15 +448,7 @@ def run_b200_arm(a):
                     "achieved": kern[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
                     "frac": kern[dom]["achieved_gbs"] / peak, "traffic": traffic, "peak_source": peak_src,
                     "alg_bytes_per_launch": kern[dom]["alg_bytes_per_obs"] * wl.n}
-        e2e = None
-        if not a.no_e2e:
-            try:
-                edt, h2d, d2h = measure_e2e(torch, wl, max(a.steps // 2, 3), 2)
-                e2e = {"value": wl.n * max(a.steps // 2, 3) / edt, "unit": UNIT, "h2d_bytes_per_step": h2d,
-                       "d2h_bytes_per_step": d2h, "n_gpus": 1,
-                       "note": "HostPipelinedEnv.step_host: pinned host frames+actions -> H2D -> ingest+observe -> D2H observations"}
-            except Exception as ex:  # never lose the line over the e2e leg
-                e2e = {"value": None, "unit": UNIT, "error": repr(ex)[:200]}
+        e2e = e2e_all
         working_set_mb = (sum(f.numel() for f in wl.frames) + wl.path.ring.numel() + wl.out.numel()) / 1e6
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
