@@ -65,6 +65,14 @@ AxisRef to_ref(const AxisOff &a, const uint32_t *base) {
 int validate(const agym_config &c) {
     if (c.n_envs <= 0 || c.frame_stack <= 0 || c.obs_h <= 0 || c.obs_w <= 0) return AGYM_ERR_INVALID_ARG;
     if (c.raw_h <= 0 || c.raw_w <= 0 || (c.raw_c != 1 && c.raw_c != 3)) return AGYM_ERR_INVALID_ARG;
+    if (c.raw_c == 3) {  // 15-bit luma weights (cv2: 9798 / 19235 / 3735): the kernels evaluate them as 16-bit IDP.2A operands
+        long sum = 0;
+        for (int i = 0; i < 3; ++i) {
+            if (c.luma_w[i] < 0 || c.luma_w[i] > 32767) return AGYM_ERR_INVALID_ARG;
+            sum += c.luma_w[i];
+        }
+        if (sum > 32768) return AGYM_ERR_INVALID_ARG;
+    }
     if (c.fov_h < 0 || c.fov_w < 0 || (c.fov_h == 0) != (c.fov_w == 0)) return AGYM_ERR_INVALID_ARG;
     if (c.periph_h < 0 || c.periph_w < 0 || (c.periph_h == 0) != (c.periph_w == 0)) return AGYM_ERR_INVALID_ARG;
     if (c.fov_h > 0) {

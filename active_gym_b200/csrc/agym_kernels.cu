@@ -155,6 +155,28 @@ __device__ __forceinline__ uint32_t word_mask(int x0, int c0, int c1) {
     return upto_hi & ~((1u << (8 * lo)) - 1u);
 }
 
+// 16 interleaved 3-channel pixels (48 bytes, 12 words) -> 16 luma bytes.
+// Y = (lw0 c0 + lw1 c1 + lw2 c2 + 16384) >> 15 (cv2's 15-bit luma, dmc_env.py:182) evaluated as
+// (2 (lw . c) + 32768) >> 16, so that Y is byte 2 of the accumulator: one PRMT gathers a pixel's three
+// bytes, two IDP.2A (16-bit weights x 8-bit channels) form the sum and PRMTs pack four results.
+// w01 = 2 lw0 | 2 lw1 << 16, w2 = 2 lw2.
+__device__ __forceinline__ uint4 luma16(const uint32_t (&w)[12], uint32_t w01, uint32_t w2) {
+    uint32_t acc[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const int j = 3 * i, wi = j >> 2, b = j & 3;  // compile time after unrolling
+        // bytes b, b+1, b+2 of the pair (w[wi], w[wi + 1]); b <= 1 stays inside one word
+        const uint32_t hi = wi + 1 < 12 ? w[wi + 1] : 0u;
+        const uint32_t q = __byte_perm(w[wi], hi, (uint32_t)(b | (b + 1) << 4 | (b + 2) << 8 | 0x4000));
+        acc[i] = __dp2a_hi(w2, q, __dp2a_lo(w01, q, 32768u));  // w2's upper half is 0: byte 3 of q does not matter
+    }
+    uint32_t o[4];
+#pragma unroll
+    for (int m = 0; m < 4; ++m)
+        o[m] = __byte_perm(__byte_perm(acc[4 * m], acc[4 * m + 1], 0x0062), __byte_perm(acc[4 * m + 2], acc[4 * m + 3], 0x0062), 0x5410);
+    return make_uint4(o[0], o[1], o[2], o[3]);
+}
+
 __device__ __forceinline__ size_t align16(size_t v) { return (v + 15) & ~size_t(15); }
 
 // Squeeze of one obs frame held in shared memory (u8) into the peripheral cache slot:
@@ -222,17 +244,7 @@ __global__ void __launch_bounds__(kThreads) k_ingest_atari(const __grid_constant
                 *reinterpret_cast<uint4 *>(w) = ld_stream128(q);
                 *reinterpret_cast<uint4 *>(w + 4) = ld_stream128(q + 16);
                 *reinterpret_cast<uint4 *>(w + 8) = ld_stream128(q + 32);
-                uint32_t out[4] = {0u, 0u, 0u, 0u};
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const int j = 3 * i;
-                    const uint32_t c0 = (w[j >> 2] >> (8 * (j & 3))) & 0xffu;
-                    const uint32_t c1 = (w[(j + 1) >> 2] >> (8 * ((j + 1) & 3))) & 0xffu;
-                    const uint32_t c2 = (w[(j + 2) >> 2] >> (8 * ((j + 2) & 3))) & 0xffu;
-                    const uint32_t yv = (p.lw0 * c0 + p.lw1 * c1 + p.lw2 * c2 + 16384u) >> 15;
-                    out[i >> 2] |= yv << (8 * (i & 3));
-                }
-                o = make_uint4(out[0], out[1], out[2], out[3]);
+                o = luma16(w, (2u * p.lw0) | ((2u * p.lw1) << 16), 2u * p.lw2);
             }
             *reinterpret_cast<uint4 *>(dst + (size_t)sr * p.raw_w + 16 * g) = o;
         }
@@ -337,48 +349,14 @@ __global__ void __launch_bounds__(kThreads) k_ingest_atari_fast(const __grid_con
     const int slot = (head[n] + 1) % p.K;
     const int rows2 = 2 * p.S_h;
     const size_t gray_bytes = (size_t)rows2 * p.raw_w;
+    // one frame's sampled rows at a time: half the shared memory, twice the CTAs per SM to hide the
+    // latency of the global loads (this kernel has no prefetch pipeline)
     uint8_t *s_gray = smem;
-    uint8_t *s_frame = s_gray + align16(2 * gray_bytes + 16);
+    uint8_t *s_frame = s_gray + align16(gray_bytes + 16);
     float *s_t1 = reinterpret_cast<float *>(s_frame + align16(p.plane + 16));
     __syncthreads();  // every thread has read head[n]
     if (tid == 0) head[n] = slot;
 
-    const int vpr = p.raw_w / 16;
-    const FastDiv fd_vpr(vpr);
-    const size_t frame_bytes = (size_t)p.raw_h * p.raw_w * CH;
-#pragma unroll 1
-    for (int fr = 0; fr < 2; ++fr) {
-        if (!(fl & (1 << fr))) continue;
-        const uint8_t *src = (fr ? fb : fa) + frame_bytes * n;
-        uint8_t *dst = s_gray + gray_bytes * fr;
-#pragma unroll 4
-        for (int t = tid; t < rows2 * vpr; t += kThreads) {
-            const int sr = fd_vpr.div(t), g = t - sr * vpr;
-            const int srow = __ldg(((sr & 1) ? p.cy_s1 : p.cy_s0) + (sr >> 1));
-            uint4 o;
-            if (CH == 1) {
-                o = ld_stream128(src + (size_t)srow * p.raw_w + 16 * g);
-            } else {
-                const uint8_t *q = src + ((size_t)srow * p.raw_w + 16 * g) * 3;
-                uint32_t w[12];
-                *reinterpret_cast<uint4 *>(w) = ld_stream128(q);
-                *reinterpret_cast<uint4 *>(w + 4) = ld_stream128(q + 16);
-                *reinterpret_cast<uint4 *>(w + 8) = ld_stream128(q + 32);
-                uint32_t out[4] = {0u, 0u, 0u, 0u};
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const int j = 3 * i;
-                    const uint32_t c0 = (w[j >> 2] >> (8 * (j & 3))) & 0xffu;
-                    const uint32_t c1 = (w[(j + 1) >> 2] >> (8 * ((j + 1) & 3))) & 0xffu;
-                    const uint32_t c2 = (w[(j + 2) >> 2] >> (8 * ((j + 2) & 3))) & 0xffu;
-                    const uint32_t yv = (p.lw0 * c0 + p.lw1 * c1 + p.lw2 * c2 + 16384u) >> 15;
-                    out[i >> 2] |= yv << (8 * (i & 3));
-                }
-                o = make_uint4(out[0], out[1], out[2], out[3]);
-            }
-            *reinterpret_cast<uint4 *>(dst + (size_t)sr * p.raw_w + 16 * g) = o;
-        }
-    }
     if (fl & AGYM_FLAG_HARD_RESET) {
         const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
         for (int k = 0; k < p.K; ++k) {
@@ -391,37 +369,64 @@ __global__ void __launch_bounds__(kThreads) k_ingest_atari_fast(const __grid_con
             }
         }
     }
-    __syncthreads();
+    if (!(fl & 3))  // no frame at all (game over before t == 2): a zero frame (atari_env.py:121,132)
+        for (int i = tid; i < p.plane / 16; i += kThreads) reinterpret_cast<uint4 *>(s_frame)[i] = make_uint4(0u, 0u, 0u, 0u);
 
+    const int vpr = p.raw_w / 16;
+    const FastDiv fd_vpr(vpr);
+    const size_t frame_bytes = (size_t)p.raw_h * p.raw_w * CH;
     const int pairs = p.S_w >> 1, segs = kThreads / pairs;
     const int g = tid / pairs, pi = tid - g * pairs;
-    if (g < segs) {
-        const int4 px = __ldg(p.cx_pair + pi);  // {aligned byte offset, PRMT selector, coef(x0), coef(x0+1)}
-        const int rows_per = (p.S_h + segs - 1) / segs;
-        const int y_end = min(p.S_h, (g + 1) * rows_per);
-        for (int y = g * rows_per; y < y_end; ++y) {
-            const int2 bs = __ldg(p.cy_bs + y);  // {b0 << 16, b1 << 16}
-            uint32_t m0 = 0u, m1 = 0u;
-#pragma unroll
-            for (int fr = 0; fr < 2; ++fr) {
-                if (!(fl & (1 << fr))) continue;
-                const uint8_t *r0 = s_gray + gray_bytes * fr + (size_t)(2 * y) * p.raw_w + px.x;
-                const uint32_t a0 = *reinterpret_cast<const uint32_t *>(r0);
-                const uint32_t a1 = *reinterpret_cast<const uint32_t *>(r0 + 4);
-                const uint32_t b0 = *reinterpret_cast<const uint32_t *>(r0 + p.raw_w);
-                const uint32_t b1 = *reinterpret_cast<const uint32_t *>(r0 + p.raw_w + 4);
-                const uint32_t qa = __byte_perm(a0, a1, (uint32_t)px.y), qb = __byte_perm(b0, b1, (uint32_t)px.y);
-                const uint32_t h00 = __dp2a_lo((uint32_t)px.z, qa, 0u), h01 = __dp2a_hi((uint32_t)px.w, qa, 0u);
-                const uint32_t h10 = __dp2a_lo((uint32_t)px.z, qb, 0u), h11 = __dp2a_hi((uint32_t)px.w, qb, 0u);
-                const uint32_t v0 = (__umulhi((uint32_t)bs.x, h00 >> 4) + __umulhi((uint32_t)bs.y, h10 >> 4) + 2u) >> 2;
-                const uint32_t v1 = (__umulhi((uint32_t)bs.x, h01 >> 4) + __umulhi((uint32_t)bs.y, h11 >> 4) + 2u) >> 2;
-                m0 = max(m0, v0);
-                m1 = max(m1, v1);
+    const int4 px = g < segs ? __ldg(p.cx_pair + pi) : make_int4(0, 0, 0, 0);  // {aligned byte offset, PRMT selector, coef(x0), coef(x0+1)}
+    const int rows_per = (p.S_h + segs - 1) / segs;
+    const int y_begin = g * rows_per, y_end = g < segs ? min(p.S_h, (g + 1) * rows_per) : y_begin;
+    bool first = true;
+#pragma unroll 1
+    for (int fr = 0; fr < 2; ++fr) {
+        if (!(fl & (1 << fr))) continue;
+        const uint8_t *src = (fr ? fb : fa) + frame_bytes * n;
+#pragma unroll 4
+        for (int t = tid; t < rows2 * vpr; t += kThreads) {
+            const int sr = fd_vpr.div(t), gg = t - sr * vpr;
+            const int srow = __ldg(((sr & 1) ? p.cy_s1 : p.cy_s0) + (sr >> 1));
+            uint4 o;
+            if (CH == 1) {
+                o = ld_stream128(src + (size_t)srow * p.raw_w + 16 * gg);
+            } else {
+                const uint8_t *q = src + ((size_t)srow * p.raw_w + 16 * gg) * 3;
+                uint32_t w[12];
+                *reinterpret_cast<uint4 *>(w) = ld_stream128(q);
+                *reinterpret_cast<uint4 *>(w + 4) = ld_stream128(q + 16);
+                *reinterpret_cast<uint4 *>(w + 8) = ld_stream128(q + 32);
+                o = luma16(w, (2u * p.lw0) | ((2u * p.lw1) << 16), 2u * p.lw2);
             }
-            *reinterpret_cast<uint16_t *>(s_frame + y * p.S_w + 2 * pi) = (uint16_t)(min(m0, 255u) | (min(m1, 255u) << 8));
+            *reinterpret_cast<uint4 *>(s_gray + (size_t)sr * p.raw_w + 16 * gg) = o;
         }
+        __syncthreads();
+        for (int y = y_begin; y < y_end; ++y) {
+            const int2 bs = __ldg(p.cy_bs + y);  // {b0 << 16, b1 << 16}
+            const uint8_t *r0 = s_gray + (size_t)(2 * y) * p.raw_w + px.x;
+            const uint32_t a0 = *reinterpret_cast<const uint32_t *>(r0);
+            const uint32_t a1 = *reinterpret_cast<const uint32_t *>(r0 + 4);
+            const uint32_t b0 = *reinterpret_cast<const uint32_t *>(r0 + p.raw_w);
+            const uint32_t b1 = *reinterpret_cast<const uint32_t *>(r0 + p.raw_w + 4);
+            const uint32_t qa = __byte_perm(a0, a1, (uint32_t)px.y), qb = __byte_perm(b0, b1, (uint32_t)px.y);
+            const uint32_t h00 = __dp2a_lo((uint32_t)px.z, qa, 0u), h01 = __dp2a_hi((uint32_t)px.w, qa, 0u);
+            const uint32_t h10 = __dp2a_lo((uint32_t)px.z, qb, 0u), h11 = __dp2a_hi((uint32_t)px.w, qb, 0u);
+            // never above 255: b0 + b1 = 2048 and h >> 4 <= 32640
+            uint32_t v0 = (__umulhi((uint32_t)bs.x, h00 >> 4) + __umulhi((uint32_t)bs.y, h10 >> 4) + 2u) >> 2;
+            uint32_t v1 = (__umulhi((uint32_t)bs.x, h01 >> 4) + __umulhi((uint32_t)bs.y, h11 >> 4) + 2u) >> 2;
+            uint16_t *o = reinterpret_cast<uint16_t *>(s_frame + y * p.S_w + 2 * pi);
+            if (!first) {  // max with the other frame's resized pixel (atari_env.py:132)
+                const uint32_t prev = *o;
+                v0 = max(v0, prev & 0xffu);
+                v1 = max(v1, prev >> 8);
+            }
+            *o = (uint16_t)(v0 | (v1 << 8));
+        }
+        first = false;
+        __syncthreads();
     }
-    __syncthreads();
     uint4 *out4 = reinterpret_cast<uint4 *>(ring + ((size_t)n * p.K + slot) * p.plane);
     for (int i = tid; i < p.plane / 16; i += kThreads) out4[i] = reinterpret_cast<const uint4 *>(s_frame)[i];
     if (pcache) {  // uniform
@@ -766,17 +771,7 @@ __global__ void __launch_bounds__(kThreads) k_ingest_dmc(const __grid_constant__
         *reinterpret_cast<uint4 *>(w) = ld_stream128(q);
         *reinterpret_cast<uint4 *>(w + 4) = ld_stream128(q + 16);
         *reinterpret_cast<uint4 *>(w + 8) = ld_stream128(q + 32);
-        uint32_t out[4] = {0u, 0u, 0u, 0u};
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            const int j = 3 * i;
-            const uint32_t c0 = (w[j >> 2] >> (8 * (j & 3))) & 0xffu;
-            const uint32_t c1 = (w[(j + 1) >> 2] >> (8 * ((j + 1) & 3))) & 0xffu;
-            const uint32_t c2 = (w[(j + 2) >> 2] >> (8 * ((j + 2) & 3))) & 0xffu;
-            const uint32_t yv = (p.lw0 * c0 + p.lw1 * c1 + p.lw2 * c2 + 16384u) >> 15;
-            out[i >> 2] |= yv << (8 * (i & 3));
-        }
-        const uint4 o = make_uint4(out[0], out[1], out[2], out[3]);
+        const uint4 o = luma16(w, (2u * p.lw0) | ((2u * p.lw1) << 16), 2u * p.lw2);
         dst[t] = o;
         if (pcache) reinterpret_cast<uint4 *>(s_frame)[t] = o;
     }
@@ -1591,7 +1586,7 @@ cudaError_t launch_ingest_atari(const DevPlan &p, const uint8_t *fa, const uint8
         return cudaGetLastError();
     }
     if (p.fast_ingest) {
-        size_t fs = a16(2 * (size_t)2 * p.S_h * p.raw_w + 16) + a16(p.plane + 16);
+        size_t fs = a16((size_t)2 * p.S_h * p.raw_w + 16) + a16(p.plane + 16);
         if (pcache) fs += sizeof(float) * p.S_h * p.p_w;
         if (p.raw_c == 1) {
             if ((e = set_smem(k_ingest_atari_fast<1>, fs)) != cudaSuccess) return e;
