@@ -15,6 +15,6 @@ $CMD > $O/plain_$TAG.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches_$TAG.csv $CMD > $O/ncu_l_$TAG.log 2>&1
 echo "ncu launches rc=$?"
 $CMD > $O/plain_$TAG.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:'k_ingest_atari_tma|k_observe_peripheral_fast' -s 8 -c 4 -f -o $O/prof_$TAG $CMD > $O/ncu_f_$TAG.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:'k_ingest_atari_tma|k_observe_peripheral' -s 8 -c 4 -f -o $O/prof_$TAG $CMD > $O/ncu_f_$TAG.log 2>&1
 echo "ncu full rc=$?"
 tail -c 600 $O/bench_${TAG}_default.json
