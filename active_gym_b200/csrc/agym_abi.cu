@@ -136,7 +136,8 @@ int agym_plan_create(const agym_config *cfg, agym_plan **out_plan) {
         ex_w = add_axis(pool, c.periph_w, c.obs_w); ex_h = add_axis(pool, c.periph_h, c.obs_h);
     }
     const int s_max = c.obs_h > c.obs_w ? c.obs_h : c.obs_w;
-    size_t o_flex = 0;
+    size_t o_flex = 0, o_flexb = 0;
+    int blur_tmax = 0;
     if (c.fov_h > 0) {
         full_w = add_axis(pool, c.fov_w, c.obs_w); full_h = add_axis(pool, c.fov_h, c.obs_h);
         // flexible fovea: for every window size r, r->f, f->r and r->S on both axes
@@ -152,6 +153,19 @@ int agym_plan_create(const agym_config *cfg, agym_plan **out_plan) {
                 }
         }
         o_flex = pool.add_i(index);
+        // composed blur operators of the flexible fovea, one per axis and window size
+        std::vector<int32_t> bindex(static_cast<size_t>(2) * (s_max + 1) * 4, 0);
+        for (int axis = 0; axis < 2; ++axis) {
+            const int f = axis == 0 ? c.fov_h : c.fov_w, S = axis == 0 ? c.obs_h : c.obs_w;
+            for (int r = 1; r <= S; ++r) {
+                const AaAxis ax = build_blur_axis(r, f);
+                int32_t *e = bindex.data() + (static_cast<size_t>(axis) * (s_max + 1) + r) * 4;
+                e[0] = static_cast<int32_t>(pool.add_i(ax.xmin)); e[1] = static_cast<int32_t>(pool.add_f(ax.w));
+                e[2] = ax.taps; e[3] = ax.n_out;
+                blur_tmax = std::max(blur_tmax, ax.taps);
+            }
+        }
+        o_flexb = pool.add_i(bindex);
     }
 
     // ---- fast-path tables (see DevPlan)
@@ -289,6 +303,8 @@ int agym_plan_create(const agym_config *cfg, agym_plan **out_plan) {
     if (c.fov_h > 0) {
         d.full_w = to_ref(full_w, base); d.full_h = to_ref(full_h, base);
         d.flex = reinterpret_cast<const FlexEntry *>(base + o_flex);
+        d.flexb = reinterpret_cast<const FlexEntry *>(base + o_flexb);
+        d.blur_tmax = blur_tmax;
     }
     d.pool_i = reinterpret_cast<const int32_t *>(base);
     d.S_max = s_max;

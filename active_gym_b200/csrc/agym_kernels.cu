@@ -447,18 +447,30 @@ __device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier
 __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+constexpr uint32_t kBackoffNs = 2000;  // suspend-time hint of the producer's try_wait
 template <bool BACKOFF = false>
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     uint32_t done = 0;
     while (!done) {
-        if (BACKOFF) __nanosleep(200);  // a lone producer lane must not burn issue slots while it waits
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done)
-            : "r"(smem_u32(bar)), "r"(parity)
-            : "memory");
+        if (BACKOFF) {
+            // a lone producer lane must not burn issue slots while it waits: let the hardware suspend
+            // the thread on the barrier (suspend-time hint) instead of polling it
+            asm volatile(
+                "{\n\t.reg .pred p;\n\t"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+                "selp.u32 %0, 1, 0, p;\n\t}"
+                : "=r"(done)
+                : "r"(smem_u32(bar)), "r"(parity), "r"(kBackoffNs)
+                : "memory");
+        } else {
+            asm volatile(
+                "{\n\t.reg .pred p;\n\t"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                "selp.u32 %0, 1, 0, p;\n\t}"
+                : "=r"(done)
+                : "r"(smem_u32(bar)), "r"(parity)
+                : "memory");
+        }
     }
 }
 // 1-D bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
@@ -1519,6 +1531,138 @@ __global__ void __launch_bounds__(kThreads) k_observe_flexible(const __grid_cons
     }
 }
 
+// Fast flexible fovea for the paste-type outputs (mask_out in place, or the zero-padded crop):
+// the blur Resize(fov_size) -> Resize(fov_res) (fov_env.py:276-280) is applied as ONE banded operator
+// per axis (host-composed, see build_blur_axis), i.e. two passes instead of four; the env's K windows
+// are staged once as aligned words; the output frame is assembled in a shared-memory tile (zeros +
+// window) and leaves as one TMA bulk store.
+template <int VARIANT>
+__global__ void __launch_bounds__(kThreads) k_observe_flexible_fast(const __grid_constant__ DevPlan p,
+                                                                    const uint8_t *__restrict__ ring,
+                                                                    const int32_t *__restrict__ head,
+                                                                    const double *__restrict__ action,
+                                                                    const int32_t *__restrict__ atype,
+                                                                    const uint8_t *__restrict__ ctrl,
+                                                                    int32_t *__restrict__ loc, int32_t *__restrict__ res,
+                                                                    int oh, int ow, uint8_t *__restrict__ out) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    __shared__ int s_win[4];
+    const int n = blockIdx.x, tid = threadIdx.x;
+    const int K = p.K, quads = p.S_w >> 2, xwm = quads + 1;
+    const int tile_bytes = K * oh * ow;
+    uint32_t *s_tile = reinterpret_cast<uint32_t *>(smem);                       // [K][oh][ow] bytes
+    uint32_t *s_x = s_tile + (tile_bytes >> 2);                                  // [K][S_h][xwm] window words
+    float *s_t1 = reinterpret_cast<float *>(s_x + K * p.S_h * xwm);              // [rh][rw]
+    float *s_ww = s_t1 + p.plane;                                                // [S_w][blur_tmax]
+    float *s_wh = s_ww + p.S_w * p.blur_tmax;                                    // [S_h][blur_tmax]
+    int32_t *s_xw = reinterpret_cast<int32_t *>(s_wh + p.S_h * p.blur_tmax);     // [S_w] first tap
+    int32_t *s_xh = s_xw + p.S_w;                                                // [S_h]
+    if (tid == 0) {
+        const int mode = ctrl ? ctrl[n] : AGYM_FOV_APPLY;
+        int r = loc[2 * n], c = loc[2 * n + 1], rh = res[2 * n], rw = res[2 * n + 1];
+        if (mode == AGYM_FOV_RESET) {
+            r = p.init_r; c = p.init_c; rh = p.f_h; rw = p.f_w;
+        } else if (mode == AGYM_FOV_APPLY) {
+            const double a0 = action[2 * n], a1 = action[2 * n + 1];
+            const int t = atype ? atype[n] : AGYM_ATYPE_FOV_LOC;
+            if (t == AGYM_ATYPE_FOV_RES) {  // fov_res = action, then re-clamp loc (fov_env.py:322-324)
+                rh = min(max((int)a0, 1), p.S_h);
+                rw = min(max((int)a1, 1), p.S_w);
+                r = clip_rint((double)r, 0.0, (double)(p.S_h - rh));
+                c = clip_rint((double)c, 0.0, (double)(p.S_w - rw));
+            } else {
+                double v0 = a0, v1 = a1;
+                if (p.relative) {
+                    v0 = (double)(r + clip_rint(a0, p.lo, p.hi));
+                    v1 = (double)(c + clip_rint(a1, p.lo, p.hi));
+                }
+                r = clip_rint(v0, 0.0, (double)(p.S_h - rh));
+                c = clip_rint(v1, 0.0, (double)(p.S_w - rw));
+            }
+        }
+        loc[2 * n] = r; loc[2 * n + 1] = c; res[2 * n] = rh; res[2 * n + 1] = rw;
+        s_win[0] = r; s_win[1] = c; s_win[2] = rh; s_win[3] = rw;
+    }
+    {   // zero frame (everything outside the window stays zero)
+        const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
+        for (int i = tid; i < (tile_bytes >> 4); i += kThreads) reinterpret_cast<uint4 *>(s_tile)[i] = z4;
+    }
+    __syncthreads();
+    const int r0 = s_win[0], c0 = s_win[1], rh = s_win[2], rw = s_win[3];
+    const int h = head[n];
+    const bool blur = rh > p.f_h;  // row dimension only (fov_env.py:286)
+    const int oy = VARIANT == AGYM_OUT_MASK ? r0 : 0, ox = VARIANT == AGYM_OUT_MASK ? c0 : 0;
+    // crop output may be narrower / shorter than the window only if the caller's pad is: clip
+    const int vh = min(rh, oh - oy), vw = min(rw, ow - ox);
+
+    // ---- stage the K windows as aligned words: row y of frame k at s_x[(k * S_h + y) * xwm ...]
+    // (byte loads straight from the ring were measured 10 % slower)
+    const int wq0 = c0 >> 2, nwx = ((c0 + rw - 1) >> 2) - wq0 + 1, cb = c0 & 3;
+    {
+        const uint32_t *ring_w = reinterpret_cast<const uint32_t *>(ring) + (size_t)n * K * (p.plane >> 2);
+        const FastDiv fd_w(nwx), fd_h(rh);
+        for (int i = tid; i < K * rh * nwx; i += kThreads) {
+            const int row = fd_w.div(i), w = i - row * nwx;
+            const int k = fd_h.div(row), y = row - k * rh;
+            int slot = h + 1 + k;
+            slot -= slot >= K ? K : 0;
+            s_x[(k * p.S_h + y) * xwm + w] = __ldg(ring_w + (size_t)slot * (p.plane >> 2) + (r0 + y) * quads + wq0 + w);
+        }
+    }
+    int tw = 1, th = 1;
+    if (blur) {  // this env's two banded operators -> shared memory
+        const FlexEntry ew = p.flexb[(p.S_max + 1) + rw], eh = p.flexb[rh];
+        tw = ew.taps; th = eh.taps;
+        const float *gw = reinterpret_cast<const float *>(p.pool_i + ew.w_off), *gh = reinterpret_cast<const float *>(p.pool_i + eh.w_off);
+        for (int i = tid; i < rw * tw; i += kThreads) s_ww[i] = __ldg(gw + i);
+        for (int i = tid; i < rh * th; i += kThreads) s_wh[i] = __ldg(gh + i);
+        for (int i = tid; i < rw; i += kThreads) s_xw[i] = __ldg(p.pool_i + ew.xmin_off + i);
+        for (int i = tid; i < rh; i += kThreads) s_xh[i] = __ldg(p.pool_i + eh.xmin_off + i);
+    }
+    __syncthreads();
+    const uint8_t *xb = reinterpret_cast<const uint8_t *>(s_x) + cb;
+    uint8_t *tb = reinterpret_cast<uint8_t *>(s_tile);
+    const FastDiv fd_rw(rw);
+    if (!blur) {  // the window itself, bit exact
+        const FastDiv fd_rh(rh);
+        for (int i = tid; i < K * rh * rw; i += kThreads) {
+            const int row = fd_rw.div(i), x = i - row * rw;
+            const int k = fd_rh.div(row), y = row - k * rh;
+            if (y < vh && x < vw) tb[(k * oh + oy + y) * ow + ox + x] = xb[((k * p.S_h + y) * xwm) * 4 + x];
+        }
+    } else {
+        for (int k = 0; k < K; ++k) {
+            // W pass: t1[y][x] = sum_t Mw[x][t] * X[y][xw[x] + t]
+            for (int i = tid; i < rh * rw; i += kThreads) {
+                const int y = fd_rw.div(i), x = i - y * rw;
+                const uint8_t *src = xb + ((k * p.S_h + y) * xwm) * 4 + s_xw[x];
+                const float *w = s_ww + x * tw;
+                float acc = 0.f;
+                for (int t = 0; t < tw; ++t) acc = fmaf(w[t], (float)src[t], acc);
+                s_t1[i] = acc;
+            }
+            __syncthreads();
+            // H pass + quantise + paste: out[y][x] = sum_t Mh[y][t] * t1[xh[y] + t][x]
+            for (int i = tid; i < rh * rw; i += kThreads) {
+                const int y = fd_rw.div(i), x = i - y * rw;
+                const float *src = s_t1 + s_xh[y] * rw + x;
+                const float *w = s_wh + y * th;
+                float acc = 0.f;
+                for (int t = 0; t < th; ++t) acc = fmaf(w[t], src[t * rw], acc);
+                if (y < vh && x < vw) tb[(k * oh + oy + y) * ow + ox + x] = (uint8_t)quant_u8(acc);
+            }
+            __syncthreads();
+        }
+    }
+    fence_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+        bulk_s2g(out + (size_t)n * tile_bytes, s_tile, (uint32_t)tile_bytes);
+        bulk_commit();
+        bulk_wait_read<0>();
+    }
+}
+
 // ------------------------------------------------------------------------------ synth
 __global__ void k_synth(uint4 *dst, size_t n_vec, uint64_t seed) {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n_vec; i += (size_t)gridDim.x * blockDim.x) {
@@ -1717,8 +1861,24 @@ cudaError_t launch_observe_peripheral(const DevPlan &p, const ExpandStd *ew, con
 cudaError_t launch_observe_flexible(const DevPlan &p, const uint8_t *ring, const int32_t *head, const double *action,
                                     const int32_t *atype, const uint8_t *ctrl, int32_t *loc, int32_t *res, int variant,
                                     int pad_h, int pad_w, uint8_t *out, cudaStream_t st) {
-    const size_t smem = sizeof(float) * 2 * (size_t)p.plane;
     cudaError_t e;
+    if (variant != AGYM_OUT_RESIZE_FULL && p.flexb && !g_disable_std) {
+        const int oh = variant == AGYM_OUT_CROP ? pad_h : p.S_h, ow = variant == AGYM_OUT_CROP ? pad_w : p.S_w;
+        const size_t tile = (size_t)p.K * oh * ow;
+        const size_t fs = tile + 4 * ((size_t)p.K * p.S_h * (p.S_w / 4 + 1) + (size_t)p.plane +
+                                      (size_t)(p.S_w + p.S_h) * p.blur_tmax + p.S_w + p.S_h);
+        if (tile % 16 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 && fs <= 200 * 1024) {
+            if (variant == AGYM_OUT_CROP) {
+                if ((e = set_smem(k_observe_flexible_fast<AGYM_OUT_CROP>, fs)) != cudaSuccess) return e;
+                k_observe_flexible_fast<AGYM_OUT_CROP><<<p.N, kThreads, fs, st>>>(p, ring, head, action, atype, ctrl, loc, res, oh, ow, out);
+            } else {
+                if ((e = set_smem(k_observe_flexible_fast<AGYM_OUT_MASK>, fs)) != cudaSuccess) return e;
+                k_observe_flexible_fast<AGYM_OUT_MASK><<<p.N, kThreads, fs, st>>>(p, ring, head, action, atype, ctrl, loc, res, oh, ow, out);
+            }
+            return cudaGetLastError();
+        }
+    }
+    const size_t smem = sizeof(float) * 2 * (size_t)p.plane;
 #define AGYM_LAUNCH_FLEX(V)                                                                              \
     if ((e = set_smem(k_observe_flexible<V>, smem)) != cudaSuccess) return e;                            \
     k_observe_flexible<V><<<p.N, kThreads, smem, st>>>(p, ring, head, action, atype, ctrl, loc, res, pad_h, pad_w, out);

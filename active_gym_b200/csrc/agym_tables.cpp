@@ -86,4 +86,39 @@ AaAxis build_aa_axis(int n_in, int n_out) {
     return ax;
 }
 
+AaAxis build_blur_axis(int r, int f) {
+    const AaAxis down = build_aa_axis(r, f), up = build_aa_axis(f, r);
+    std::vector<double> dense(static_cast<size_t>(r) * r, 0.0);
+    for (int y = 0; y < r; ++y)
+        for (int a = 0; a < up.taps; ++a) {
+            const double wa = up.w[static_cast<size_t>(y) * up.taps + a];
+            if (wa == 0.0) continue;
+            const int j = up.xmin[y] + a;
+            for (int b = 0; b < down.taps; ++b)
+                dense[static_cast<size_t>(y) * r + down.xmin[j] + b] += wa * down.w[static_cast<size_t>(j) * down.taps + b];
+        }
+    AaAxis ax;
+    ax.n_in = r; ax.n_out = r;
+    ax.xmin.resize(r);
+    std::vector<int> last(r);
+    int taps = 1;
+    for (int y = 0; y < r; ++y) {
+        int lo = 0, hi = r - 1;
+        while (lo < r - 1 && dense[static_cast<size_t>(y) * r + lo] == 0.0) ++lo;
+        while (hi > lo && dense[static_cast<size_t>(y) * r + hi] == 0.0) --hi;
+        ax.xmin[y] = lo; last[y] = hi;
+        taps = std::max(taps, hi - lo + 1);
+    }
+    ax.taps = taps;
+    ax.w.assign(static_cast<size_t>(r) * taps, 0.f);
+    for (int y = 0; y < r; ++y) {
+        int lo = ax.xmin[y];
+        if (lo + taps > r) lo = r - taps;  // keep the window inside: zeros in front
+        for (int x = ax.xmin[y]; x <= last[y]; ++x)
+            ax.w[static_cast<size_t>(y) * taps + (x - lo)] = static_cast<float>(dense[static_cast<size_t>(y) * r + x]);
+        ax.xmin[y] = lo;
+    }
+    return ax;
+}
+
 }  // namespace agym

@@ -31,4 +31,9 @@ struct AaAxis {
 };
 AaAxis build_aa_axis(int n_in, int n_out);
 
+// The flexible fovea's blur along one axis, Resize(f) followed by Resize(r) (fov_env.py:276-280), as ONE
+// banded r x r operator M = A(f -> r) * B(r -> f): the reference keeps floats between the two resamples,
+// so the composition is the same linear map (weights multiplied and summed in double).
+AaAxis build_blur_axis(int r, int f);
+
 }  // namespace agym
