@@ -1,0 +1,160 @@
+"""GPU: the persistent / pipelined kernels at batch sizes where every CTA walks several envs
+(TMA ingest, peripheral std kernel with its mbarrier ring and batched fov_loc, flexible fast path),
+with ragged per-env flags and fovea controls, against the CPU oracle for EVERY env; and the host
+pipeline's env shards against the unsharded path."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import agym_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+TOL = 0.5 + 1e-2
+S = (84, 84)
+
+
+def _path(n, K=4, raw=(210, 160, 1), luma=None, **kw):
+    from active_gym_b200 import ObservationPath, LUMA_RGB
+    return ObservationPath(n, K, S, raw, luma=luma or LUMA_RGB, **kw)
+
+
+def _np(t):
+    torch.cuda.synchronize()
+    return t.cpu().numpy()
+
+
+def _flags(rng, n):
+    choices = np.array([3, 3, 3, 3, 1, 0, 5, 1 | 4, 8, 3 | 4, 2], np.uint8)  # incl. frame B only, idle, resets
+    return choices[rng.integers(0, len(choices), n)]
+
+
+def _frames(rng, n):
+    # cheap but structured: per-env random 8x8 blocks upsampled + noise, so that resize errors would show
+    base = rng.integers(0, 256, (n, 27, 20), dtype=np.uint8).repeat(8, 1).repeat(8, 2)[:, :210, :160]
+    return base ^ rng.integers(0, 32, (n, 210, 160), dtype=np.uint8)
+
+
+@pytest.mark.parametrize("n", [445, 1500])
+def test_tma_ingest_many_envs_per_cta_ragged(n):
+    rng = np.random.default_rng(n)
+    K = 4
+    p = _path(n, K, fov_size=(30, 30), peripheral_res=(20, 20))  # with the squeeze cache
+    ring, head = orc.new_state(n, K, S)
+    for step in range(4):
+        fa, fb = _frames(rng, n), _frames(rng, n)
+        fl = np.full(n, 5, np.uint8) if step == 0 else _flags(rng, n)
+        p.ingest_atari(fa, fb, fl)
+        orc.ingest_atari(fa, fb, fl, ring, head)
+        assert np.array_equal(_np(p.head), head), step
+        assert np.array_equal(_np(p.ring), ring), step
+    # the cache written by the ingest kernel == the squeeze recomputed from the ring (uncached kernel)
+    a = rng.integers(0, 55, (n, 2)).astype(np.float64)
+    cached = p.observe_peripheral(a)
+    direct = p.observe_peripheral(None, ctrl=np.full(n, 2, np.uint8), use_cache=False)
+    assert (cached.int() - direct.int()).abs().max().item() <= 1
+
+
+@pytest.mark.parametrize("K,n", [(4, 700), (3, 611), (4, 297)])
+def test_peripheral_std_kernel_all_envs_vs_oracle(K, n):
+    rng = np.random.default_rng(100 + n)
+    fov, periph = (30, 30), (20, 20)
+    p = _path(n, K, fov_size=fov, peripheral_res=periph, fov_init_loc=(7, 11), sensory_action_mode="relative",
+              sensory_action_space=(-10.0, 10.0))
+    ring, head = orc.new_state(n, K, S)
+    loc = np.zeros((n, 2), np.int32)
+    for step in range(5):
+        fa, fb = _frames(rng, n), _frames(rng, n)
+        fl = np.full(n, 5, np.uint8) if step == 0 else _flags(rng, n)
+        p.ingest_atari(fa, fb, fl)
+        orc.ingest_atari(fa, fb, fl, ring, head)
+        a = rng.uniform(-14, 14, (n, 2))
+        a[::5] = rng.integers(-10, 11, (len(a[::5]), 2)) + 0.5  # ties: round half to even after the clip
+        # fovea control: reset everywhere at step 0, afterwards a mix of apply / reset / keep
+        ctrl = np.full(n, 1, np.uint8) if step == 0 else rng.choice(np.array([0, 0, 0, 1, 2], np.uint8), n)
+        apply_, reset = ctrl == 0, ctrl == 1
+        new = loc.copy()
+        orc.update_loc(a, new, obs_size=S, fov_size=fov, relative=True, lo=-10.0, hi=10.0)
+        loc[apply_] = new[apply_]
+        loc[reset] = (7, 11)
+        got = _np(p.observe_peripheral(a, ctrl=ctrl))
+        assert np.array_equal(_np(p.loc), loc), step
+        want = orc.observe_peripheral(ring, head, loc, fov, periph)
+        assert np.abs(got.astype(np.float64) - want).max() <= TOL, step
+        full = orc.stack(ring, head)
+        for e in range(0, n, 13):  # the pasted fovea is bit exact
+            r, c = loc[e]
+            assert np.array_equal(got[e, :, r:r + 30, c:c + 30], full[e, :, r:r + 30, c:c + 30])
+
+
+def test_peripheral_std_kernel_other_fovea_sizes():
+    # the std kernel takes any fovea at the 84/20 geometry: non-multiple-of-4 widths, tall, tiny, huge
+    rng = np.random.default_rng(5)
+    n, K = 333, 4
+    for fov in [(30, 30), (17, 45), (61, 9), (83, 83), (1, 1)]:
+        p = _path(n, K, fov_size=fov, peripheral_res=(20, 20), sensory_action_mode="absolute")
+        ring, head = orc.new_state(n, K, S)
+        for step in range(K + 1):
+            fa, fb = _frames(rng, n), _frames(rng, n)
+            fl = np.full(n, 5 if step == 0 else 3, np.uint8)
+            p.ingest_atari(fa, fb, fl)
+            orc.ingest_atari(fa, fb, fl, ring, head)
+        loc = np.zeros((n, 2), np.int32)
+        a = rng.integers(-5, 90, (n, 2)).astype(np.float64)
+        orc.update_loc(a, loc, obs_size=S, fov_size=fov)
+        got = _np(p.observe_peripheral(a)).astype(np.float64)
+        assert np.array_equal(_np(p.loc), loc), fov
+        assert np.abs(got - orc.observe_peripheral(ring, head, loc, fov, (20, 20))).max() <= TOL, fov
+
+
+@pytest.mark.parametrize("variant,pad", [("mask", None), ("crop", None), ("crop", (52, 56))])
+def test_flexible_fast_path_many_envs(variant, pad):
+    rng = np.random.default_rng(21)
+    n, K, fov = 300, 4, (30, 30)
+    p = _path(n, K, fov_size=fov, sensory_action_mode="relative", sensory_action_space=(-10.0, 10.0))
+    ring, head = orc.new_state(n, K, S)
+    for step in range(K + 1):
+        fa, fb = _frames(rng, n), _frames(rng, n)
+        fl = np.full(n, 5 if step == 0 else 3, np.uint8)
+        p.ingest_atari(fa, fb, fl)
+        orc.ingest_atari(fa, fb, fl, ring, head)
+    loc = np.zeros((n, 2), np.int32)
+    res = np.tile(np.array([fov], np.int32), (n, 1))
+    p.observe_flexible(None, variant=variant, ctrl="reset", pad=pad)
+    for step in range(4):
+        atype = rng.integers(0, 2, n).astype(np.int32)
+        hi = 51 if pad else 85
+        a = np.where(atype[:, None] == 1, rng.integers(1, hi, (n, 2)), rng.uniform(-12, 12, (n, 2))).astype(np.float64)
+        orc.update_loc(a, loc, obs_size=S, fov_size=fov, relative=True, lo=-10.0, hi=10.0, atype=atype, res=res)
+        got = _np(p.observe_flexible(a, atype, variant=variant, pad=pad)).astype(np.float64)
+        want = orc.observe_flexible(ring, head, loc, res, fov, variant=variant, pad=pad)
+        assert np.array_equal(_np(p.loc), loc) and np.array_equal(_np(p.res), res), step
+        assert got.shape == want.shape
+        assert np.abs(got - want).max() <= TOL, step
+        sharp = res[:, 0] <= fov[0]  # not blurred: bit exact (fov_env.py:286 looks at rows only)
+        assert np.array_equal(got[sharp], want[sharp])
+
+
+def test_host_pipeline_shards_equal_unsharded_path():
+    from active_gym_b200.hostpipe import HostPipelinedEnv
+    rng = np.random.default_rng(9)
+    n, K = 203, 4  # not a multiple of the shard count
+    kw = dict(fov_size=(30, 30), sensory_action_mode="relative", sensory_action_space=(-10.0, 10.0), peripheral_res=(20, 20))
+    env = HostPipelinedEnv(n, K, S, (210, 160, 1), kind="atari", wrapper="peripheral", shards=7, **kw)
+    ref = _path(n, K, **kw)
+    hf = env.alloc_host_frames()
+    for t in hf:
+        t.numpy()[...] = _frames(rng, n)
+    obs, loc = env.reset_host(hf)
+    ref.ingest_atari(hf[0].numpy(), hf[0].numpy(), np.full(n, 5, np.uint8))
+    want = ref.observe_peripheral(None, ctrl="reset")
+    assert np.array_equal(obs.numpy(), _np(want)) and np.array_equal(loc.numpy(), _np(ref.loc))
+    for step in range(3):
+        for t in hf:
+            t.numpy()[...] = _frames(rng, n)
+        a = rng.integers(-10, 11, (n, 2)).astype(np.float64)
+        obs, loc = env.step_host(hf, a)
+        ref.ingest_atari(hf[0].numpy(), hf[1].numpy(), np.full(n, 3, np.uint8))
+        want = ref.observe_peripheral(a)
+        assert np.array_equal(obs.numpy(), _np(want)), step
+        assert np.array_equal(loc.numpy(), _np(ref.loc)), step
