@@ -905,6 +905,54 @@ __global__ void __launch_bounds__(kThreads) k_observe_fixed(const __grid_constan
     }
 }
 
+// Crop variant, one WARP per env (8 envs per CTA): a (K, f_h, f_w) observation is only a few KB, so
+// a CTA per env spends its life in the latency chain loc update -> loads -> stores; here every lane
+// owns ~total/128 output words whose byte gathers are all independent and in flight together.
+__global__ void __launch_bounds__(kThreads) k_observe_fixed_crop_warp(const __grid_constant__ DevPlan p,
+                                                                      const uint8_t *__restrict__ ring,
+                                                                      const int32_t *__restrict__ head,
+                                                                      const double *__restrict__ action,
+                                                                      const uint8_t *__restrict__ ctrl,
+                                                                      int32_t *__restrict__ loc, uint8_t *__restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int n = blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+    if (n >= p.N) return;
+    int r0 = 0, c0 = 0;
+    if (lane == 0) update_loc_fixed(p, n, action, ctrl, loc, r0, c0);
+    r0 = __shfl_sync(0xffffffffu, r0, 0);
+    c0 = __shfl_sync(0xffffffffu, c0, 0);
+    const int h = head[n];
+    const int per_k = p.f_h * p.f_w, words = (p.K * per_k) >> 2;
+    const FastDiv fd_k(per_k), fd_w(p.f_w);
+    const uint8_t *env_ring = ring + (size_t)n * p.K * p.plane + (size_t)r0 * p.S_w + c0;
+    uint32_t *dst = reinterpret_cast<uint32_t *>(out + (size_t)n * p.K * per_k);
+#pragma unroll 4
+    for (int t = lane; t < words; t += 32) {
+        const int b = 4 * t;
+        int k = fd_k.div(b), rem = b - k * per_k;
+        int y = fd_w.div(rem), x = rem - y * p.f_w;
+        int slot = h + 1 + k;
+        slot -= slot >= p.K ? p.K : 0;
+        const uint8_t *src = env_ring + (size_t)slot * p.plane + y * p.S_w;
+        uint32_t word = 0u;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            word |= (uint32_t)__ldg(src + x) << (8 * i);
+            if (++x == p.f_w) {  // next fovea row, possibly next frame
+                x = 0;
+                src += p.S_w;
+                if (++y == p.f_h) {
+                    y = 0;
+                    ++k;
+                    slot = slot + 1 == p.K ? 0 : slot + 1;
+                    src = env_ring + (size_t)slot * p.plane;
+                }
+            }
+        }
+        dst[t] = word;
+    }
+}
+
 // ------------------------------------------------------------------- observe: peripheral
 // FixedFovealPeripheralEnv._get_fov_state (fov_env.py:375-388):
 //   out = Resize(obs)(Resize(peripheral_res)(full)); out[fovea] = full[fovea].
@@ -1768,7 +1816,9 @@ cudaError_t launch_stack(const DevPlan &p, const uint8_t *ring, const int32_t *h
 cudaError_t launch_observe_fixed(const DevPlan &p, const uint8_t *ring, const int32_t *head, const double *action,
                                  const uint8_t *ctrl, int32_t *loc, int variant, uint8_t *out, cudaStream_t st) {
     cudaError_t e;
-    if (variant == AGYM_OUT_CROP) {
+    if (variant == AGYM_OUT_CROP && (p.K * p.f_h * p.f_w) % 4 == 0 && !g_disable_std) {
+        k_observe_fixed_crop_warp<<<(p.N + kThreads / 32 - 1) / (kThreads / 32), kThreads, 0, st>>>(p, ring, head, action, ctrl, loc, out);
+    } else if (variant == AGYM_OUT_CROP) {
         k_observe_fixed<AGYM_OUT_CROP><<<p.N, kThreads, 0, st>>>(p, ring, head, action, ctrl, loc, out);
     } else if (variant == AGYM_OUT_MASK) {
         k_observe_fixed<AGYM_OUT_MASK><<<p.N, kThreads, 0, st>>>(p, ring, head, action, ctrl, loc, out);
