@@ -14,6 +14,9 @@
  *     `h_` parameters are HOST pointers.  A plan owns only its small coefficient tables.
  *   - all device work is enqueued on `stream` (a cudaStream_t passed as void*); no
  *     function synchronises unless its name ends in `_host`.
+ *   - buffers should be 16-byte aligned (any cudaMalloc / torch allocation is): the TMA bulk-copy paths
+ *     (cached squeeze in, observation tile out) need it; unaligned buffers are served by the slower
+ *     table-driven kernels, never rejected.
  *   - u8 pixels everywhere: the reference's normalised float value is
  *     float64(float32(u)/255) for the u8 value u.
  *
