@@ -1592,7 +1592,7 @@ __global__ void __launch_bounds__(kThreads) k_observe_flexible_fast(const __grid
                                                                     const int32_t *__restrict__ atype,
                                                                     const uint8_t *__restrict__ ctrl,
                                                                     int32_t *__restrict__ loc, int32_t *__restrict__ res,
-                                                                    int oh, int ow, uint8_t *__restrict__ out) {
+                                                                    int oh, int ow, int t1_cap, uint8_t *__restrict__ out) {
     extern __shared__ __align__(16) uint8_t smem[];
     __shared__ int s_win[4];
     const int n = blockIdx.x, tid = threadIdx.x;
@@ -1601,7 +1601,7 @@ __global__ void __launch_bounds__(kThreads) k_observe_flexible_fast(const __grid
     uint32_t *s_tile = reinterpret_cast<uint32_t *>(smem);                       // [K][oh][ow] bytes
     uint32_t *s_x = s_tile + (tile_bytes >> 2);                                  // [K][S_h][xwm] window words
     float *s_t1 = reinterpret_cast<float *>(s_x + K * p.S_h * xwm);              // [rh][rw]
-    float *s_ww = s_t1 + p.plane;                                                // [S_w][blur_tmax]
+    float *s_ww = s_t1 + t1_cap;                                                 // [S_w][blur_tmax]
     float *s_wh = s_ww + p.S_w * p.blur_tmax;                                    // [S_h][blur_tmax]
     int32_t *s_xw = reinterpret_cast<int32_t *>(s_wh + p.S_h * p.blur_tmax);     // [S_w] first tap
     int32_t *s_xh = s_xw + p.S_w;                                                // [S_h]
@@ -1679,25 +1679,43 @@ __global__ void __launch_bounds__(kThreads) k_observe_flexible_fast(const __grid
             if (y < vh && x < vw) tb[(k * oh + oy + y) * ow + ox + x] = xb[((k * p.S_h + y) * xwm) * 4 + x];
         }
     } else {
-        for (int k = 0; k < K; ++k) {
+        // t1 rows are padded to a multiple of 4 floats so that the H pass reads float4; as many frames
+        // per pass as fit (all K for windows up to ~50 x 52), so an env costs 2 barriers instead of 2K
+        const int rwp = (rw + 3) & ~3, per = rh * rwp;
+        const int kg = K * per <= t1_cap ? K : 1;
+        const FastDiv fd_fr(rh * rw), fd_q(rwp >> 2), fd_frq(rh * (rwp >> 2));
+        for (int k0 = 0; k0 < K; k0 += kg) {
             // W pass: t1[y][x] = sum_t Mw[x][t] * X[y][xw[x] + t]
-            for (int i = tid; i < rh * rw; i += kThreads) {
-                const int y = fd_rw.div(i), x = i - y * rw;
-                const uint8_t *src = xb + ((k * p.S_h + y) * xwm) * 4 + s_xw[x];
+            for (int i = tid; i < kg * rh * rw; i += kThreads) {
+                const int kk = fd_fr.div(i), rem = i - kk * rh * rw;
+                const int y = fd_rw.div(rem), x = rem - y * rw;
+                const uint8_t *src = xb + (((k0 + kk) * p.S_h + y) * xwm) * 4 + s_xw[x];
                 const float *w = s_ww + x * tw;
                 float acc = 0.f;
                 for (int t = 0; t < tw; ++t) acc = fmaf(w[t], (float)src[t], acc);
-                s_t1[i] = acc;
+                s_t1[kk * per + y * rwp + x] = acc;
             }
             __syncthreads();
-            // H pass + quantise + paste: out[y][x] = sum_t Mh[y][t] * t1[xh[y] + t][x]
-            for (int i = tid; i < rh * rw; i += kThreads) {
-                const int y = fd_rw.div(i), x = i - y * rw;
-                const float *src = s_t1 + s_xh[y] * rw + x;
+            // H pass, 4 columns per thread + quantise + paste: out[y][x] = sum_t Mh[y][t] * t1[xh[y] + t][x]
+            for (int i = tid; i < kg * rh * (rwp >> 2); i += kThreads) {
+                const int kk = fd_frq.div(i), rem = i - kk * rh * (rwp >> 2);
+                const int y = fd_q.div(rem), x0 = 4 * (rem - y * (rwp >> 2));
+                const float *src = s_t1 + kk * per + s_xh[y] * rwp + x0;
                 const float *w = s_wh + y * th;
-                float acc = 0.f;
-                for (int t = 0; t < th; ++t) acc = fmaf(w[t], src[t * rw], acc);
-                if (y < vh && x < vw) tb[(k * oh + oy + y) * ow + ox + x] = (uint8_t)quant_u8(acc);
+                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int t = 0; t < th; ++t) {
+                    const float4 v = *reinterpret_cast<const float4 *>(src + t * rwp);
+                    const float wt = w[t];
+                    acc.x = fmaf(wt, v.x, acc.x); acc.y = fmaf(wt, v.y, acc.y);
+                    acc.z = fmaf(wt, v.z, acc.z); acc.w = fmaf(wt, v.w, acc.w);
+                }
+                if (y < vh) {
+                    uint8_t *o = tb + ((k0 + kk) * oh + oy + y) * ow + ox + x0;
+                    if (x0 < vw) o[0] = (uint8_t)quant_u8(acc.x);
+                    if (x0 + 1 < vw) o[1] = (uint8_t)quant_u8(acc.y);
+                    if (x0 + 2 < vw) o[2] = (uint8_t)quant_u8(acc.z);
+                    if (x0 + 3 < vw) o[3] = (uint8_t)quant_u8(acc.w);
+                }
             }
             __syncthreads();
         }
@@ -1915,15 +1933,17 @@ cudaError_t launch_observe_flexible(const DevPlan &p, const uint8_t *ring, const
     if (variant != AGYM_OUT_RESIZE_FULL && p.flexb && !g_disable_std) {
         const int oh = variant == AGYM_OUT_CROP ? pad_h : p.S_h, ow = variant == AGYM_OUT_CROP ? pad_w : p.S_w;
         const size_t tile = (size_t)p.K * oh * ow;
-        const size_t fs = tile + 4 * ((size_t)p.K * p.S_h * (p.S_w / 4 + 1) + (size_t)p.plane +
+        // t1: one padded window of any size (S_h x S_w), or all K frames of windows up to ~50 x 52
+        const int t1_cap = std::max(p.S_h * ((p.S_w + 3) & ~3), std::min(p.K * 50 * 52, p.K * p.S_h * ((p.S_w + 3) & ~3)));
+        const size_t fs = tile + 4 * ((size_t)p.K * p.S_h * (p.S_w / 4 + 1) + (size_t)t1_cap +
                                       (size_t)(p.S_w + p.S_h) * p.blur_tmax + p.S_w + p.S_h);
         if (tile % 16 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 && fs <= 200 * 1024) {
             if (variant == AGYM_OUT_CROP) {
                 if ((e = set_smem(k_observe_flexible_fast<AGYM_OUT_CROP>, fs)) != cudaSuccess) return e;
-                k_observe_flexible_fast<AGYM_OUT_CROP><<<p.N, kThreads, fs, st>>>(p, ring, head, action, atype, ctrl, loc, res, oh, ow, out);
+                k_observe_flexible_fast<AGYM_OUT_CROP><<<p.N, kThreads, fs, st>>>(p, ring, head, action, atype, ctrl, loc, res, oh, ow, t1_cap, out);
             } else {
                 if ((e = set_smem(k_observe_flexible_fast<AGYM_OUT_MASK>, fs)) != cudaSuccess) return e;
-                k_observe_flexible_fast<AGYM_OUT_MASK><<<p.N, kThreads, fs, st>>>(p, ring, head, action, atype, ctrl, loc, res, oh, ow, out);
+                k_observe_flexible_fast<AGYM_OUT_MASK><<<p.N, kThreads, fs, st>>>(p, ring, head, action, atype, ctrl, loc, res, oh, ow, t1_cap, out);
             }
             return cudaGetLastError();
         }
