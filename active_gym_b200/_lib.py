@@ -26,7 +26,7 @@ EXPORTS = (
     "agym_abi_version", "agym_status_string", "agym_plan_create", "agym_plan_destroy",
     "agym_plan_ring_bytes", "agym_plan_pcache_bytes", "agym_ingest_atari", "agym_ingest_dmc",
     "agym_stack", "agym_observe_fixed", "agym_observe_peripheral", "agym_observe_flexible",
-    "agym_synth_frames", "agym_table_cv2", "agym_table_aa",
+    "agym_synth_frames", "agym_table_cv2", "agym_table_aa", "agym_normalize",
 )
 
 
@@ -69,6 +69,7 @@ def lib() -> C.CDLL:
     L.agym_observe_peripheral.argtypes = [vp] * 9
     L.agym_observe_flexible.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp, vp]
     L.agym_synth_frames.argtypes = [vp, sz, u64, vp]
+    L.agym_normalize.argtypes = [vp, sz, i32, vp, vp]
     L.agym_table_cv2.argtypes = [i32, i32, i32, vp, vp, vp]
     L.agym_table_aa.argtypes = [i32, i32, vp, vp, sz, vp]
     if L.agym_abi_version() != ABI_VERSION:

@@ -439,6 +439,12 @@ int agym_table_aa(int n_in, int n_out, int32_t *h_xmin, float *h_w, size_t w_cap
     return AGYM_OK;
 }
 
+int agym_normalize(const uint8_t *d_src, size_t n_bytes, int dtype, void *d_dst, void *stream) {
+    if (!d_src || !d_dst || n_bytes % 16 != 0 || dtype < AGYM_DTYPE_F32 || dtype > AGYM_DTYPE_BF16) return AGYM_ERR_INVALID_ARG;
+    if ((reinterpret_cast<uintptr_t>(d_src) & 15) || (reinterpret_cast<uintptr_t>(d_dst) & 15)) return AGYM_ERR_INVALID_ARG;
+    return ret(launch_normalize(d_src, n_bytes, dtype, d_dst, as_stream(stream)));
+}
+
 int agym_synth_frames(uint8_t *d_dst, size_t n_bytes, uint64_t seed, void *stream) {
     if (!d_dst || n_bytes % 16 != 0) return AGYM_ERR_INVALID_ARG;
     return ret(launch_synth(d_dst, n_bytes, seed, as_stream(stream)));

@@ -84,6 +84,7 @@ cudaError_t launch_observe_peripheral(const DevPlan &p, const ExpandStd *ew, con
 cudaError_t launch_observe_flexible(const DevPlan &p, const uint8_t *ring, const int32_t *head, const double *action,
                                     const int32_t *atype, const uint8_t *ctrl, int32_t *loc, int32_t *res, int variant,
                                     int pad_h, int pad_w, uint8_t *out, cudaStream_t st);
+cudaError_t launch_normalize(const uint8_t *src, size_t n, int dtype, void *dst, cudaStream_t st);
 cudaError_t launch_synth(uint8_t *dst, size_t n, uint64_t seed, cudaStream_t st);
 
 }  // namespace agym

@@ -213,6 +213,22 @@ class ObservationPath:
                        "agym_observe_flexible")
         return out
 
+    _NORM_DTYPES = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2}
+
+    def normalize(self, obs: torch.Tensor, dtype: torch.dtype = torch.float32, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """u8 observations -> the reference's normalised float32(u)/255 (atari_env.py:75, dmc_env.py:183) on the
+        device; float32 is bit-identical to the reference's value, float16 / bfloat16 round it once more."""
+        if obs.dtype != torch.uint8 or obs.device != self.device or not obs.is_contiguous():
+            raise TypeError("normalize expects a contiguous uint8 tensor on the path's device")
+        if obs.numel() % 16 != 0:
+            raise ValueError("the number of pixels must be a multiple of 16")
+        if out is None:
+            out = torch.empty(obs.shape, dtype=dtype, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self._L.agym_normalize(_ptr(obs), obs.numel(), self._NORM_DTYPES[dtype], _ptr(out), self._stream()),
+                       "agym_normalize")
+        return out
+
     def synth_frames(self, out: torch.Tensor, seed: int) -> torch.Tensor:
         """Fills a device u8 tensor with hashed pseudo-random bytes (benchmark input)."""
         assert out.dtype == torch.uint8 and out.is_contiguous() and out.device == self.device

@@ -151,6 +151,15 @@ AGYM_API int agym_observe_flexible(const agym_plan *plan, const uint8_t *d_ring,
 AGYM_API int agym_table_cv2(int n_src, int n_dst, int zero_frac_at_border, int32_t *h_s0, int32_t *h_s1, int32_t *h_coef);
 AGYM_API int agym_table_aa(int n_in, int n_out, int32_t *h_xmin, float *h_w, size_t w_capacity, int32_t *taps);
 
+/* Consumer-side convenience: u8 observations -> the reference's normalised value
+ * float32(u) / 255 (atari_env.py:75, dmc_env.py:183).  AGYM_DTYPE_F32 is bit-identical to the reference's
+ * float32; F16 / BF16 round that value once more.  n_bytes: number of pixels, a multiple of 16; both
+ * pointers 16-byte aligned. */
+#define AGYM_DTYPE_F32 0
+#define AGYM_DTYPE_F16 1
+#define AGYM_DTYPE_BF16 2
+AGYM_API int agym_normalize(const uint8_t *d_src, size_t n_bytes, int dtype, void *d_dst, void *stream);
+
 /* Benchmark / test helper: fills d_dst with a counter-based hash of (seed, byte index). */
 AGYM_API int agym_synth_frames(uint8_t *d_dst, size_t n_bytes, uint64_t seed, void *stream);
 

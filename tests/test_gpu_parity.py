@@ -209,3 +209,17 @@ def test_full_size_properties_config2_and_config4():
     sel = np.arange(0, n4, 2048)
     want = orc.observe_peripheral(q.ring[sel].cpu().numpy(), q.head[sel].cpu().numpy(), q.loc[sel].cpu().numpy(), (30, 30), (20, 20))
     assert np.abs(cached[sel].cpu().numpy().astype(np.float64) - want).max() <= TOL
+
+
+def test_normalize_is_the_reference_float32_value():
+    # atari_env.py:75 / dmc_env.py:183: float32(u) / 255, bit for bit; f16 / bf16 round that value once
+    rng = np.random.default_rng(4)
+    p = _path(8, 4, fov_size=(30, 30))
+    u = torch.from_numpy(rng.integers(0, 256, (8, 4, 30, 30), dtype=np.uint8)).cuda()
+    want = u.cpu().numpy().astype(np.float32) / np.float32(255.0)
+    got = _np(p.normalize(u))
+    assert got.dtype == np.float32 and np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    assert torch.equal(p.normalize(u, torch.float16).cpu(), torch.from_numpy(want).to(torch.float16))
+    assert torch.equal(p.normalize(u, torch.bfloat16).cpu(), torch.from_numpy(want).to(torch.bfloat16))
+    allv = torch.arange(256, dtype=torch.uint8).repeat(2).cuda()  # every value
+    assert np.array_equal(_np(p.normalize(allv))[:256], np.arange(256, dtype=np.float32) / np.float32(255.0))
