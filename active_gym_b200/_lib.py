@@ -26,7 +26,7 @@ EXPORTS = (
     "agym_abi_version", "agym_status_string", "agym_plan_create", "agym_plan_destroy",
     "agym_plan_ring_bytes", "agym_plan_pcache_bytes", "agym_ingest_atari", "agym_ingest_dmc",
     "agym_stack", "agym_observe_fixed", "agym_observe_peripheral", "agym_observe_flexible",
-    "agym_synth_frames", "agym_table_cv2", "agym_table_aa", "agym_normalize",
+    "agym_synth_frames", "agym_table_cv2", "agym_table_aa", "agym_normalize", "agym_plan_used_rows", "agym_ingest_atari_packed",
 )
 
 
@@ -64,6 +64,8 @@ def lib() -> C.CDLL:
     L.agym_plan_pcache_bytes.argtypes = [vp]
     L.agym_ingest_atari.argtypes = [vp] * 8
     L.agym_ingest_dmc.argtypes = [vp] * 7
+    L.agym_ingest_atari_packed.argtypes = [vp] * 8
+    L.agym_plan_used_rows.argtypes = [vp, vp, i32]
     L.agym_stack.argtypes = [vp] * 5
     L.agym_observe_fixed.argtypes = [vp, vp, vp, vp, vp, vp, i32, vp, vp]
     L.agym_observe_peripheral.argtypes = [vp] * 9

@@ -15,6 +15,8 @@ using namespace agym;
 struct agym_plan {
     agym_config cfg;
     DevPlan dev;
+    DevPlan dev_packed;             // same, for frames that carry only the raw rows the resize samples
+    std::vector<int32_t> used_rows; // those rows, ascending (host)
     ExpandStd expand_std;  // host copy, see agym_kernels.cuh
     void *pool = nullptr;  // device: every coefficient table, one allocation
     size_t pool_bytes = 0;
@@ -130,6 +132,19 @@ int agym_plan_create(const agym_config *cfg, agym_plan **out_plan) {
     const Cv2Axis cx = build_cv2_axis(c.raw_w, c.obs_w, true), cy = build_cv2_axis(c.raw_h, c.obs_h, false);
     const size_t o_xs0 = pool.add_i(cx.s0), o_xs1 = pool.add_i(cx.s1), o_xcf = pool.add_i(cx.coef);
     const size_t o_ys0 = pool.add_i(cy.s0), o_ys1 = pool.add_i(cy.s1), o_ycf = pool.add_i(cy.coef);
+    // packed frames: only the raw rows some output row samples, in ascending order (cv2 reads two of every
+    // 2.5 rows for 210 -> 84, so a fifth of a frame never has to cross PCIe)
+    std::vector<int32_t> used(cy.s0);
+    used.insert(used.end(), cy.s1.begin(), cy.s1.end());
+    std::sort(used.begin(), used.end());
+    used.erase(std::unique(used.begin(), used.end()), used.end());
+    std::vector<int32_t> ys0p(cy.s0.size()), ys1p(cy.s1.size());
+    for (size_t y = 0; y < cy.s0.size(); ++y) {
+        ys0p[y] = static_cast<int32_t>(std::lower_bound(used.begin(), used.end(), cy.s0[y]) - used.begin());
+        ys1p[y] = static_cast<int32_t>(std::lower_bound(used.begin(), used.end(), cy.s1[y]) - used.begin());
+    }
+    const size_t o_ys0p = pool.add_i(ys0p), o_ys1p = pool.add_i(ys1p);
+    pl->used_rows = used;
     AxisOff sq_w{}, sq_h{}, ex_w{}, ex_h{}, full_w{}, full_h{};
     if (c.periph_h > 0) {
         sq_w = add_axis(pool, c.obs_w, c.periph_w); sq_h = add_axis(pool, c.obs_h, c.periph_h);
@@ -309,20 +324,23 @@ int agym_plan_create(const agym_config *cfg, agym_plan **out_plan) {
     d.pool_i = reinterpret_cast<const int32_t *>(base);
     d.S_max = s_max;
     d.fast_ingest = fast_ingest;
-    for (int u = 1; u <= 4; ++u) {  // row span of the largest unit when the output rows are cut into u units
-        d.tma_span_rows[u - 1] = 0;
-        if (c.obs_h % u != 0) continue;
-        const int R = c.obs_h / u;
-        int span = 0;
-        bool monotone = true;
-        for (int k = 0; k < u; ++k) {
-            const int lo = cy.s0[k * R], hi = cy.s1[k * R + R - 1];
-            for (int y = k * R; y < k * R + R; ++y) monotone = monotone && cy.s0[y] >= lo && cy.s1[y] <= hi;
-            span = std::max(span, hi - lo + 1);
+    auto spans = [&](const std::vector<int32_t> &s0, const std::vector<int32_t> &s1, int32_t *out4) {
+        for (int u = 1; u <= 4; ++u) {  // row span of the largest unit when the output rows are cut into u units
+            out4[u - 1] = 0;
+            if (c.obs_h % u != 0) continue;
+            const int R = c.obs_h / u;
+            int span = 0;
+            bool monotone = true;
+            for (int k = 0; k < u; ++k) {
+                const int lo = s0[k * R], hi = s1[k * R + R - 1];
+                for (int y = k * R; y < k * R + R; ++y) monotone = monotone && s0[y] >= lo && s1[y] <= hi;
+                span = std::max(span, hi - lo + 1);
+            }
+            // a stage holds both frames' spans; keep two stages well inside one SM's shared memory
+            if (monotone && 2 * (2 * (static_cast<size_t>(span) * c.raw_w + 16)) <= 96 * 1024) out4[u - 1] = span;
         }
-        // a stage holds both frames' spans; keep two stages well inside one SM's shared memory
-        if (monotone && 2 * (2 * (static_cast<size_t>(span) * c.raw_w + 16)) <= 96 * 1024) d.tma_span_rows[u - 1] = span;
-    }
+    };
+    spans(cy.s0, cy.s1, d.tma_span_rows);
     if (fast_ingest) {
         d.cx_pair = reinterpret_cast<const int4 *>(base + o_pair);
         d.cy_bs = reinterpret_cast<const int2 *>(base + o_ybs);
@@ -341,6 +359,11 @@ int agym_plan_create(const agym_config *cfg, agym_plan **out_plan) {
         d.exh_i0 = ip(o_ehi); d.exh_w0 = reinterpret_cast<const float *>(base + o_ehw);
         d.exw_w1 = reinterpret_cast<const float *>(base + o_eww1);
     }
+    pl->dev_packed = d;
+    pl->dev_packed.cy_s0 = ip(o_ys0p);
+    pl->dev_packed.cy_s1 = ip(o_ys1p);
+    pl->dev_packed.raw_h = static_cast<int32_t>(used.size());
+    spans(ys0p, ys1p, pl->dev_packed.tma_span_rows);
     *out_plan = pl;
     return AGYM_OK;
 }
@@ -368,6 +391,24 @@ int agym_ingest_atari(const agym_plan *plan, const uint8_t *d_frames_a, const ui
     if (d_pcache && plan->cfg.periph_h == 0) return AGYM_ERR_INVALID_ARG;
     if (plan->cfg.raw_w % 16 != 0) return AGYM_ERR_UNSUPPORTED;  // rows are staged as 16-byte vectors
     return ret(launch_ingest_atari(plan->dev, d_frames_a, d_frames_b, d_flags, d_ring, d_head, d_pcache, as_stream(stream)));
+}
+
+int agym_plan_used_rows(const agym_plan *plan, int32_t *h_rows, int32_t capacity) {
+    if (!plan) return AGYM_ERR_INVALID_ARG;
+    const int32_t n = static_cast<int32_t>(plan->used_rows.size());
+    if (h_rows) {
+        if (capacity < n) return AGYM_ERR_INVALID_ARG;
+        std::memcpy(h_rows, plan->used_rows.data(), sizeof(int32_t) * n);
+    }
+    return n;
+}
+
+int agym_ingest_atari_packed(const agym_plan *plan, const uint8_t *d_rows_a, const uint8_t *d_rows_b,
+                             const uint8_t *d_flags, uint8_t *d_ring, int32_t *d_head, float *d_pcache, void *stream) {
+    if (!plan || !d_rows_a || !d_rows_b || !d_flags || !d_ring || !d_head) return AGYM_ERR_INVALID_ARG;
+    if (d_pcache && plan->cfg.periph_h == 0) return AGYM_ERR_INVALID_ARG;
+    if (plan->cfg.raw_w % 16 != 0) return AGYM_ERR_UNSUPPORTED;
+    return ret(launch_ingest_atari(plan->dev_packed, d_rows_a, d_rows_b, d_flags, d_ring, d_head, d_pcache, as_stream(stream)));
 }
 
 int agym_ingest_dmc(const agym_plan *plan, const uint8_t *d_frames, const uint8_t *d_flags, uint8_t *d_ring,

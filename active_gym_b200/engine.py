@@ -128,6 +128,29 @@ class ObservationPath:
             _lib.check(self._L.agym_ingest_atari(self._plan, _ptr(fa), _ptr(fb), _ptr(fl), _ptr(self.ring), _ptr(self.head),
                                                  _ptr(self.pcache), self._stream()), "agym_ingest_atari")
 
+    @property
+    def used_rows(self) -> np.ndarray:
+        """Raw rows the resize samples, ascending (atari_env.py:74 reads two rows per output row)."""
+        if getattr(self, "_used_rows", None) is None:
+            n = self._L.agym_plan_used_rows(self._plan, None, 0)
+            buf = (C.c_int32 * n)()
+            self._L.agym_plan_used_rows(self._plan, buf, n)
+            self._used_rows = np.frombuffer(buf, dtype=np.int32).copy()
+        return self._used_rows
+
+    def ingest_atari_packed(self, rows_a, rows_b, flags) -> None:
+        """``ingest_atari`` on frames that carry only ``used_rows`` (shape (N, len(used_rows), raw_w[, 3])):
+        a transport optimisation for host frame sources; bit-identical results."""
+        h, w, c = self.raw_shape
+        nu = len(self.used_rows)
+        fa = self._as_frames(rows_a, (nu, w, c))
+        fb = self._as_frames(rows_b, (nu, w, c))
+        fl = self._dev_u8(flags, (self.n_envs,))
+        with torch.cuda.device(self.device):
+            _lib.check(self._L.agym_ingest_atari_packed(self._plan, _ptr(fa), _ptr(fb), _ptr(fl), _ptr(self.ring),
+                                                        _ptr(self.head), _ptr(self.pcache), self._stream()),
+                       "agym_ingest_atari_packed")
+
     def ingest_dmc(self, frames, flags) -> None:
         """DMCEnv._get_obs (pixel, grey) + stack logic (dmc_env.py:175-183, 228-230)."""
         h, w, c = self.raw_shape

@@ -319,37 +319,60 @@ def time_kernel(torch, fn, reps, warmup=3):
     return sum(ts) / len(ts), min(ts)
 
 
-def measure_e2e(torch, wl, steps, warmup, shards=32):
-    """The same env step through the public batched-env API with HOST buffers: every step copies the
-    step's raw frames + actions from pinned host memory to the GPU and the observations back to
-    pinned host memory (all inside the timed region).  The batch is cut into `shards` env shards,
-    each with its own stream, so the H2D of one shard overlaps the kernels / D2H of another."""
-    import active_gym_b200 as ag
+def measure_e2e(torch, wl, steps, warmup, shards=16):
+    """The same env step through the public host-buffer API (HostPipelinedEnv): every step copies the step's
+    raw frames + actions from pinned host memory to the GPU and the observations back to pinned host memory,
+    all inside the timed region.  The env batch is driven as two groups of N/2 envs, double buffered the way
+    host-simulator samplers are: wait A(t) -> [agent] -> submit A(t+1) -> wait B(t) -> submit B(t+1) ..., so
+    a group's actions still depend on its own previous observations while the PCIe link stays busy across
+    step boundaries.  Each group is cut into `shards` env shards with their own streams (H2D of one shard
+    overlaps the kernels / D2H of another); only the raw rows the resize samples cross PCIe."""
     from active_gym_b200.hostpipe import HostPipelinedEnv
     w = wl.w
-    env = HostPipelinedEnv.from_workload(w, wl.n, wl.device, shards=shards, obs_size=S)
+    halves = [wl.n // 2, wl.n - wl.n // 2]
+    envs = [HostPipelinedEnv.from_workload(w, m, wl.device, shards=shards, obs_size=S) for m in halves]
     rng = np.random.default_rng(7)
     n_host = 2
-    host_frames = [env.alloc_host_frames() for _ in range(n_host)]
-    for hf in host_frames:
-        for t in hf:
-            t.numpy()[...] = rng.integers(0, 256, t.shape, dtype=np.uint8)
-    act = rng.integers(-10, 11, (wl.n, 2)).astype(np.float64) if w["mode"] == "relative" else rng.integers(0, 55, (wl.n, 2)).astype(np.float64)
-    atype = np.zeros(wl.n, np.int32)
-    env.reset_host(host_frames[0])
-    i = [0]
+    host_frames = [[env.alloc_host_frames() for _ in range(n_host)] for env in envs]
+    for per_env in host_frames:
+        for hf in per_env:
+            for t in hf:
+                t.numpy()[...] = rng.integers(0, 256, t.shape, dtype=np.uint8)
+    acts = [rng.integers(-10, 11, (m, 2)).astype(np.float64) if w["mode"] == "relative" else
+            rng.integers(0, 55, (m, 2)).astype(np.float64) for m in halves]
+    atypes = [np.zeros(m, np.int32) for m in halves]
+    for env, hf in zip(envs, host_frames):
+        env.reset_host(hf[0])
+    checks = [0]
 
-    def one():
-        env.step_host(host_frames[i[0] % n_host], act, atype)
-        i[0] += 1
+    def submit(g, t):
+        envs[g].submit_host(host_frames[g][t % n_host], acts[g], atypes[g])
+
+    def wait(g):
+        obs, loc = envs[g].wait_host()          # observations are in host memory now
+        checks[0] += int(obs[0, 0, 0, 0]) + int(loc[0, 0])
+
+    t = 0
+    for g in (0, 1):
+        submit(g, t)
     for _ in range(warmup):
-        one()
+        t += 1
+        for g in (0, 1):
+            wait(g); submit(g, t)
     torch.cuda.synchronize()
+    for g in (0, 1):
+        wait(g)
+    # timed: `steps` full steps of both groups, first submits to last wait
     t0 = time.perf_counter()
-    for _ in range(steps):
-        one()          # step_host returns after the observations are in host memory
+    for g in (0, 1):
+        submit(g, t + 1)
+    for k in range(steps - 1):
+        for g in (0, 1):
+            wait(g); submit(g, t + 2 + k)
+    for g in (0, 1):
+        wait(g)
     dt = time.perf_counter() - t0
-    return dt, env.h2d_bytes_per_step, env.d2h_bytes_per_step
+    return dt, sum(e.h2d_bytes_per_step for e in envs), sum(e.d2h_bytes_per_step for e in envs)
 
 
 def run_b200_arm(a):
@@ -423,8 +446,9 @@ def run_b200_arm(a):
         if err is None and edt < 1e29:
             e2e_all = {"value": wl.n * world * e_steps / edt, "unit": UNIT, "h2d_bytes_per_step": h2d * world,
                        "d2h_bytes_per_step": d2h * world, "n_gpus": world, "steps": e_steps,
-                       "note": "HostPipelinedEnv.step_host on every rank: pinned host frames+actions -> H2D -> "
-                               "ingest+observe -> D2H observations; host wall clock, max over ranks"}
+                       "note": "HostPipelinedEnv submit_host / wait_host on every rank, two env groups double buffered: "
+                               "pinned host frames (sampled rows only) + actions -> H2D -> ingest+observe -> D2H "
+                               "observations; host wall clock, max over ranks"}
         else:
             e2e_all = {"value": None, "unit": UNIT, "error": err or "a rank failed"}
     line = None

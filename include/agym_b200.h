@@ -111,6 +111,16 @@ AGYM_API int agym_ingest_atari(const agym_plan *plan, const uint8_t *d_frames_a,
                       const uint8_t *d_flags, uint8_t *d_ring, int32_t *d_head, float *d_pcache,
                       void *stream);
 
+/* Transport optimisation for host frame sources: cv2's bilinear resize reads only two raw rows per output
+ * row (atari_env.py:74; 168 of 210 rows for 210 -> 84), so a frame may be shipped without the rows that are
+ * never sampled.  agym_plan_used_rows returns their count and, if h_rows != NULL (capacity entries), the
+ * ascending row indices; agym_ingest_atari_packed is agym_ingest_atari on frames laid out as
+ * u8 [N][n_used_rows][raw_w][raw_c] holding exactly those rows.  Results are bit-identical. */
+AGYM_API int agym_plan_used_rows(const agym_plan *plan, int32_t *h_rows, int32_t capacity);
+AGYM_API int agym_ingest_atari_packed(const agym_plan *plan, const uint8_t *d_rows_a, const uint8_t *d_rows_b,
+                             const uint8_t *d_flags, uint8_t *d_ring, int32_t *d_head, float *d_pcache,
+                             void *stream);
+
 /* Replaces DMCEnv._get_obs (pixel, grey branch) + stack logic (dmc_env.py:175-183, 193-195,
  * 206-207, 228-230): luma of the rendered frame -> push.  d_frames: u8 [N][S_h][S_w][3]. */
 AGYM_API int agym_ingest_dmc(const agym_plan *plan, const uint8_t *d_frames, const uint8_t *d_flags,

@@ -158,3 +158,43 @@ def test_host_pipeline_shards_equal_unsharded_path():
         want = ref.observe_peripheral(a)
         assert np.array_equal(obs.numpy(), _np(want)), step
         assert np.array_equal(loc.numpy(), _np(ref.loc)), step
+
+
+@pytest.mark.parametrize("ch,n", [(1, 700), (3, 40)])
+def test_packed_rows_ingest_is_bit_identical(ch, n):
+    # frames that carry only the raw rows the resize samples (agym_ingest_atari_packed)
+    rng = np.random.default_rng(31)
+    K = 4
+    a = _path(n, K, raw=(210, 160, ch), fov_size=(30, 30), peripheral_res=(20, 20))
+    b = _path(n, K, raw=(210, 160, ch), fov_size=(30, 30), peripheral_res=(20, 20))
+    rows = a.used_rows
+    assert len(rows) == 168 and rows[0] == 0 and rows[-1] == 209 and 2 not in rows
+    for step in range(3):
+        shape = (n, 210, 160) if ch == 1 else (n, 210, 160, 3)
+        fa = rng.integers(0, 256, shape, dtype=np.uint8)
+        fb = rng.integers(0, 256, shape, dtype=np.uint8)
+        fl = np.full(n, 5, np.uint8) if step == 0 else _flags(rng, n)
+        a.ingest_atari(fa, fb, fl)
+        b.ingest_atari_packed(np.ascontiguousarray(fa[:, rows]), np.ascontiguousarray(fb[:, rows]), fl)
+        assert torch.equal(a.ring, b.ring) and torch.equal(a.head, b.head), step
+        assert torch.equal(a.pcache, b.pcache), step
+
+
+def test_host_pipeline_packed_h2d_equals_full_frames():
+    from active_gym_b200.hostpipe import HostPipelinedEnv, periodic_run
+    rng = np.random.default_rng(13)
+    n, K = 150, 4
+    kw = dict(fov_size=(30, 30), sensory_action_mode="relative", sensory_action_space=(-10.0, 10.0), peripheral_res=(20, 20))
+    packed = HostPipelinedEnv(n, K, S, (210, 160, 1), kind="atari", wrapper="peripheral", shards=4, packed_h2d=True, **kw)
+    full = HostPipelinedEnv(n, K, S, (210, 160, 1), kind="atari", wrapper="peripheral", shards=3, packed_h2d=False, **kw)
+    assert packed.run == (5, 3, 4) and full.run is None
+    assert packed.h2d_bytes_per_step < 0.81 * full.h2d_bytes_per_step
+    assert periodic_run(np.arange(84), 84) is None  # nothing to skip: no packed mode
+    hp, hf = packed.alloc_host_frames(), full.alloc_host_frames()
+    for step in range(4):
+        for tp, tf in zip(hp, hf):
+            tf.numpy()[...] = _frames(rng, n)
+            tp.numpy()[...] = tf.numpy()
+        a = rng.integers(-10, 11, (n, 2)).astype(np.float64)
+        (op, lp), (of, lf) = (packed.reset_host(hp), full.reset_host(hf)) if step == 0 else (packed.step_host(hp, a), full.step_host(hf, a))
+        assert np.array_equal(op.numpy(), of.numpy()) and np.array_equal(lp.numpy(), lf.numpy()), step
