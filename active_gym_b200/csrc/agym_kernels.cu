@@ -1033,9 +1033,6 @@ __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
 __device__ __forceinline__ void cp_async4(void *smem_dst, const void *gmem_src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src));
 }
-__device__ __forceinline__ void cp_async16_s(uint32_t smem_addr, const void *gmem_src) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gmem_src));
-}
 __device__ __forceinline__ void cp_async4_s(uint32_t smem_addr, const void *gmem_src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_addr), "l"(gmem_src));
 }
@@ -1297,7 +1294,7 @@ __global__ void __launch_bounds__(((StdGeom::Q * StdGeom::SEG * K + 31) / 32) * 
                              const uint8_t *__restrict__ ctrl, int32_t *__restrict__ loc, uint8_t *__restrict__ out) {
     using Gm = StdGeom;
     constexpr int S = Gm::S, P = Gm::P, Q = Gm::Q, R = Gm::R;
-    constexpr int NB = Q * Gm::SEG * K, NWARP = (NB + 31) / 32;
+    constexpr int NB = Q * Gm::SEG * K;
     constexpr int PP = P * P, PLANE_W = S * S / 4;
     constexpr int NBUF = 3, DIST = 2, LOC_RING = 128;
     extern __shared__ __align__(16) uint8_t smem[];
