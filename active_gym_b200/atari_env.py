@@ -68,7 +68,7 @@ class AtariVecEnv(Env):
         self.training = True
         if source is None:
             from .sources import ALEPool
-            source = ALEPool(args, self.num_envs)
+            source = ALEPool(args, self.num_envs, workers=getattr(args, "sim_workers", 1))
         self.source = source
         self.path = _path_from_args(args, self.num_envs, tuple(source.raw_shape),
                                     getattr(args, "luma", LUMA_RGB), device or getattr(args, "device", None))

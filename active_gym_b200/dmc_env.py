@@ -55,7 +55,7 @@ class DMCVecEnv(Env):
         self.clip_reward = args.clip_reward
         if source is None:
             from .sources import DMCPool
-            source = DMCPool(args, self.num_envs)
+            source = DMCPool(args, self.num_envs, workers=getattr(args, "sim_workers", 1))
         self.source = source
         # dmc_env.py:182 applies COLOR_BGR2GRAY to an RGB render: channel 0 gets the blue weight
         self.path = _path_from_args(args, self.num_envs, tuple(source.raw_shape), LUMA_DMC,

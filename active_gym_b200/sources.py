@@ -22,6 +22,39 @@ import torch
 from ._lib import FLAG_FRAME_A, FLAG_FRAME_B, FLAG_HARD_RESET, FLAG_IDLE
 
 
+class _Workers:
+    """Runs ``fn(i)`` for every env index on ``workers`` host threads (contiguous index blocks).  The
+    simulators are C/C++ libraries behind ctypes / pybind calls that release the GIL, so env stepping
+    scales with host cores; every env writes only its own rows of the pinned staging buffers."""
+
+    def __init__(self, num_envs: int, workers: int):
+        self.num_envs = int(num_envs)
+        self.workers = max(1, min(int(workers), self.num_envs))
+        self.pool = None
+        if self.workers > 1:
+            from concurrent.futures import ThreadPoolExecutor
+            self.pool = ThreadPoolExecutor(max_workers=self.workers, thread_name_prefix="agym-sim")
+            b = np.linspace(0, self.num_envs, self.workers + 1).astype(int)
+            self.blocks = [(int(lo), int(hi)) for lo, hi in zip(b[:-1], b[1:]) if hi > lo]
+
+    def run(self, fn) -> None:
+        if self.pool is None:
+            for i in range(self.num_envs):
+                fn(i)
+            return
+
+        def block(r):
+            for i in range(*r):
+                fn(i)
+        for f in [self.pool.submit(block, r) for r in self.blocks]:
+            f.result()  # re-raises a worker's exception
+
+    def close(self) -> None:
+        if self.pool is not None:
+            self.pool.shutdown(wait=True)
+            self.pool = None
+
+
 def _pinned(shape, dtype=torch.uint8) -> torch.Tensor:
     t = torch.zeros(shape, dtype=dtype)
     if torch.cuda.is_available():
@@ -34,10 +67,11 @@ class ALEPool:
 
     raw_shape = (210, 160, 1)
 
-    def __init__(self, args, num_envs: int, ale_factory: Optional[Callable[[int], object]] = None):
+    def __init__(self, args, num_envs: int, ale_factory: Optional[Callable[[int], object]] = None, workers: int = 1):
         self.num_envs = int(num_envs)
         self.action_repeat = int(args.action_repeat)
         self.training = True
+        self._workers = _Workers(self.num_envs, workers)
         if ale_factory is None:
             import atari_py  # third-party; absent in this image
 
@@ -67,17 +101,25 @@ class ALEPool:
 
     def reset(self, mask: Optional[np.ndarray] = None):
         """atari_env.py:84-113 minus the buffer work.  Returns (frames, frames, flags)."""
-        for i, ale in enumerate(self.ales):
+        # the reference draws its no-op count from the global `random` (atari_env.py:96); draw them here,
+        # serially and in env order, so that worker threads do not change the stream
+        noops = [None] * self.num_envs
+        for i in range(self.num_envs):
+            if (mask is None or mask[i]) and not self.life_termination[i]:
+                noops[i] = random.randrange(30)
+
+        def one(i):
+            ale = self.ales[i]
             if mask is not None and not mask[i]:
                 self.flags[i] = FLAG_IDLE
-                continue
+                return
             if self.life_termination[i]:
                 self.life_termination[i] = False
                 ale.act(0)
                 self.flags[i] = FLAG_FRAME_A
             else:
                 ale.reset_game()
-                for _ in range(random.randrange(30)):
+                for _ in range(noops[i]):
                     ale.act(0)
                     if ale.game_over():
                         ale.reset_game()
@@ -91,6 +133,7 @@ class ALEPool:
                     ale.reset_game()
             self._screen(ale, self._fa[i])
             self.lives[i] = ale.lives()
+        self._workers.run(one)
         return self.frames_a, self.frames_a, self.flags
 
     def step(self, motor_action: Sequence[int]):
@@ -98,7 +141,9 @@ class ALEPool:
         n = self.num_envs
         reward, done = np.zeros(n, np.float64), np.zeros(n, bool)
         motor_action = np.asarray(motor_action).reshape(n)
-        for i, ale in enumerate(self.ales):
+
+        def one(i):
+            ale = self.ales[i]
             fl, r, d = 0, 0, False
             for t in range(self.action_repeat):
                 r += ale.act(self.actions.get(int(motor_action[i])))
@@ -116,14 +161,19 @@ class ALEPool:
                     d = True
                 self.lives[i] = lives
             self.flags[i], reward[i], done[i] = fl, r, d
+        self._workers.run(one)
         return self.frames_a, self.frames_b, self.flags, reward, done
+
+    def close(self):
+        self._workers.close()
 
 
 class DMCPool:
     """Host pool of dm_control tasks; renders at obs_size (dmc_env.py:175-180)."""
 
-    def __init__(self, args, num_envs: int, env_factory: Optional[Callable[[int], object]] = None):
+    def __init__(self, args, num_envs: int, env_factory: Optional[Callable[[int], object]] = None, workers: int = 1):
         self.num_envs, self.action_repeat = int(num_envs), int(args.action_repeat)
+        self._workers = _Workers(self.num_envs, workers)
         self.obs_size, self.camera_id = tuple(args.obs_size), args.camera_id
         if env_factory is None:
             from dm_control import suite  # third-party; absent in this image
@@ -153,13 +203,14 @@ class DMCPool:
         self._f[i] = self.envs[i].physics.render(height=h, width=w, camera_id=self.camera_id)
 
     def reset(self, mask=None):
-        for i, env in enumerate(self.envs):
+        def one(i):
             if mask is not None and not mask[i]:
                 self.flags[i] = FLAG_IDLE
-                continue
-            self.last_time_steps[i] = env.reset()
+                return
+            self.last_time_steps[i] = self.envs[i].reset()
             self._render(i)
             self.flags[i] = FLAG_FRAME_A | FLAG_HARD_RESET
+        self._workers.run(one)
         return self.frames, self.flags
 
     def extra_info(self):
@@ -171,7 +222,9 @@ class DMCPool:
         n = self.num_envs
         reward, done = np.zeros(n, np.float64), np.zeros(n, bool)
         motor_action = np.asarray(motor_action, np.float32).reshape(n, -1)
-        for i, env in enumerate(self.envs):
+
+        def one(i):
+            env = self.envs[i]
             a = self._convert_action(motor_action[i])
             r = 0
             for _ in range(self.action_repeat):  # dmc_env.py:218-223
@@ -183,7 +236,11 @@ class DMCPool:
             self.last_time_steps[i] = ts
             self._render(i)
             reward[i], self.flags[i] = r, FLAG_FRAME_A
+        self._workers.run(one)
         return self.frames, self.flags, reward, done
+
+    def close(self):
+        self._workers.close()
 
 
 class SyntheticAtariSource:

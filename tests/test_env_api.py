@@ -216,3 +216,41 @@ def test_batched_env_equals_independent_envs_and_masked_reset():
     assert torch.equal(env.path.ring[keep], before_ring[keep]) and torch.equal(env.path.loc[keep], before_loc[keep])
     assert info["fov_loc"][1].tolist() == [3, 5] and info["ep_len"].tolist() == [3, 0, 3, 3, 0, 3]
     assert int(env.path.ring[1].ne(0).any(dim=-1).any(dim=-1).sum()) == 1, "hard reset leaves one non-zero frame"
+
+
+def test_ale_pool_worker_threads_do_not_change_results():
+    """N fake ALEs with their own scripts: 4 worker threads == serial, frame for frame (the no-op counts of
+    the reference's reset come from the global `random` and are drawn serially in env order)."""
+    from active_gym_b200 import AtariEnvArgs
+    from active_gym_b200.sources import ALEPool
+    scr = gr.screens("atari")
+    n = 11
+
+    def factory_for(offsets):
+        def factory(i):
+            s = rh.ScreenScript(scr[..., None], game_over_at=(40 + 7 * i, 90 + i), lives_at={25 + i: 2})
+            s.acts = offsets[i]
+            rh.ScreenScript.current = s
+            return rh._FakeALE()
+        return factory
+
+    args = AtariEnvArgs(game="boxing", seed=0, obs_size=(84, 84), frame_stack=4, action_repeat=4)
+    runs = []
+    for workers in (1, 4):
+        random.seed(123)
+        pool = ALEPool(args, n, ale_factory=factory_for([3 * i for i in range(n)]), workers=workers)
+        log = []
+        fa, fb, fl = pool.reset()
+        log.append((fa.numpy().copy(), fl.copy()))
+        for step in range(12):
+            fa, fb, fl, r, d = pool.step(np.zeros(n, np.int64))
+            log.append((fa.numpy().copy(), fb.numpy().copy(), fl.copy(), r.copy(), d.copy()))
+            if d.any():
+                fa, fb, fl = pool.reset(mask=d)
+                log.append((fa.numpy().copy(), fl.copy()))
+        pool.close()
+        runs.append(log)
+    assert len(runs[0]) == len(runs[1])
+    for a, b in zip(*runs):
+        for x, y in zip(a, b):
+            assert np.array_equal(x, y)
