@@ -198,3 +198,39 @@ def test_host_pipeline_packed_h2d_equals_full_frames():
         a = rng.integers(-10, 11, (n, 2)).astype(np.float64)
         (op, lp), (of, lf) = (packed.reset_host(hp), full.reset_host(hf)) if step == 0 else (packed.step_host(hp, a), full.step_host(hf, a))
         assert np.array_equal(op.numpy(), of.numpy()) and np.array_equal(lp.numpy(), lf.numpy()), step
+
+
+@pytest.mark.parametrize("obs,fov,periph", [((64, 64), (20, 24), (16, 16)), ((96, 96), (30, 30), (24, 20)), ((84, 84), (30, 30), (21, 28))])
+def test_other_geometries_use_the_table_driven_kernels(obs, fov, periph):
+    # nothing here is the standard 84/20 geometry: generic / v2 kernels, other TMA unit counts
+    from active_gym_b200 import ObservationPath
+    rng = np.random.default_rng(obs[0] + periph[0])
+    n, K = 450, 4
+    p = ObservationPath(n, K, obs, (210, 160, 1), fov_size=fov, peripheral_res=periph, sensory_action_mode="relative",
+                        sensory_action_space=(-6.0, 6.0))
+    ring, head = orc.new_state(n, K, obs)
+    loc = np.zeros((n, 2), np.int32)
+    p.observe_peripheral(None, ctrl="reset")
+    for step in range(K + 1):
+        fa, fb = _frames(rng, n), _frames(rng, n)
+        fl = np.full(n, 5, np.uint8) if step == 0 else _flags(rng, n)
+        p.ingest_atari(fa, fb, fl)
+        orc.ingest_atari(fa, fb, fl, ring, head)  # the oracle takes the obs size from the ring's shape
+        assert np.array_equal(_np(p.ring), ring), step
+        a = rng.uniform(-8, 8, (n, 2))
+        orc.update_loc(a, loc, obs_size=obs, fov_size=fov, relative=True, lo=-6.0, hi=6.0)
+        got = _np(p.observe_peripheral(a)).astype(np.float64)
+        assert np.array_equal(_np(p.loc), loc), step
+        assert np.abs(got - orc.observe_peripheral(ring, head, loc, fov, periph)).max() <= TOL, step
+    crop = _np(p.observe_fixed(None, ctrl=np.full(n, 2, np.uint8)))
+    assert np.array_equal(crop, orc.observe_fixed(ring, head, loc, fov))
+    mask = _np(p.observe_fixed(None, variant="mask", ctrl=np.full(n, 2, np.uint8)))
+    assert np.array_equal(mask, orc.observe_fixed(ring, head, loc, fov, variant="mask"))
+    res = np.tile(np.array([fov], np.int32), (n, 1))
+    p.res[:] = torch.from_numpy(res).cuda()
+    atype = np.ones(n, np.int32)
+    a = rng.integers(1, obs[0] + 1, (n, 2)).astype(np.float64)
+    orc.update_loc(a, loc, obs_size=obs, fov_size=fov, relative=True, lo=-6.0, hi=6.0, atype=atype, res=res)
+    got = _np(p.observe_flexible(a, atype, variant="mask")).astype(np.float64)
+    assert np.array_equal(_np(p.res), res) and np.array_equal(_np(p.loc), loc)
+    assert np.abs(got - orc.observe_flexible(ring, head, loc, res, fov, variant="mask")).max() <= TOL
