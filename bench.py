@@ -471,6 +471,7 @@ def run_b200_arm(a):
         roofline = {"bound": "hbm", "kernel": f"{dom} ({'k_ingest' if dom == 'ingest' else 'k_observe'}_* of {a.workload})",
                     "achieved": kern[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
                     "frac": kern[dom]["achieved_gbs"] / peak, "traffic": traffic, "peak_source": peak_src,
+                    "peak_nominal": 8000.0, "frac_nominal": kern[dom]["achieved_gbs"] / 8000.0,
                     "alg_bytes_per_launch": kern[dom]["alg_bytes_per_obs"] * wl.n}
         e2e = e2e_all
         working_set_mb = (sum(f.numel() for f in wl.frames) + wl.path.ring.numel() + wl.out.numel()) / 1e6
