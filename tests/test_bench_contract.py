@@ -1,0 +1,44 @@
+"""CPU: the bench.py contract that can be checked without a GPU — the reference arm prints ONE JSON line with
+the agreed keys, and the b200 arm refuses to run (loudly) when there is no CUDA device."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _run(*args, env=None):
+    e = dict(os.environ)
+    e.update(env or {})
+    return subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), *args], capture_output=True, text=True,
+                          cwd=ROOT, env=e, timeout=600)
+
+
+def test_reference_arm_prints_one_json_line_with_the_contract_keys():
+    r = _run("--impl", "reference", "--steps", "2", "--warmup", "1", "--cpu-seconds", "0.6")
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "foveal_obs_per_sec" and d["unit"] == "obs/s"
+    assert d["higher_is_better"] is True and d["steps"] == 2 and d["warmup"] == 1 and d["value"] > 0
+    assert d["config"]["workload"] == "atari_peripheral"
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "sample" in cb
+    assert d["e2e"] == {"value": d["value"], "unit": "obs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_reference_arm_other_ranks_exit_quietly():
+    r = _run("--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1", env={"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"})
+    assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="needs a machine without a GPU")
+def test_b200_arm_fails_loudly_without_a_gpu():
+    r = _run("--steps", "1", "--warmup", "1", "--no-cpu-baseline", "--no-e2e")
+    assert r.returncode != 0
+    assert "CUDA" in (r.stderr + r.stdout) or "cuda" in (r.stderr + r.stdout)
