@@ -745,10 +745,29 @@ __global__ void __launch_bounds__(kIngestThreads, 3) k_ingest_atari_tma(const __
                     if (tt < taps) acc0 = fmaf(w[tt], t[tt * pw], acc0);
                     dst[o] = acc0 + acc1;
                 };
-                const FastDiv fd_pw(pw);
-                for (int o = tid; o < total; o += kThreads) {
-                    const int i = fd_pw.div(o);
-                    one(o, i, o - i * pw);
+                if ((pw & 3) == 0) {
+                    // four adjacent columns per thread: one LDS.128 of t1 and one weight per tap serve 4 FFMA
+                    const int nq = pw >> 2;
+                    const FastDiv fd_nq(nq);
+                    for (int o = tid; o < p.p_h * nq; o += kThreads) {
+                        const int i = fd_nq.div(o), j = 4 * (o - i * nq);
+                        const float *w = s_sqh + i * taps;
+                        const float *t = s_t1 + s_sqx[i] * pw + j;
+                        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                        for (int tt = 0; tt < taps; ++tt) {
+                            const float4 v = *reinterpret_cast<const float4 *>(t + tt * pw);
+                            const float wt = w[tt];
+                            acc.x = fmaf(wt, v.x, acc.x); acc.y = fmaf(wt, v.y, acc.y);
+                            acc.z = fmaf(wt, v.z, acc.z); acc.w = fmaf(wt, v.w, acc.w);
+                        }
+                        *reinterpret_cast<float4 *>(dst + i * pw + j) = acc;
+                    }
+                } else {
+                    const FastDiv fd_pw(pw);
+                    for (int o = tid; o < total; o += kThreads) {
+                        const int i = fd_pw.div(o);
+                        one(o, i, o - i * pw);
+                    }
                 }
             }
         }
