@@ -771,7 +771,9 @@ __global__ void __launch_bounds__(kIngestThreads, 3) k_ingest_atari_tma(const __
                 }
             }
         }
-        consumer_sync();  // s_frame / s_t1 are reused by the next env
+        // with the cache, no barrier here: the H pass reads only s_t1, which the next env rewrites after its own
+        // 'frame complete' barrier, and s_frame was last read before the barrier between the two passes
+        if (!pcache) consumer_sync();  // s_frame is rewritten by the next env's first unit
         }
     }
 }
