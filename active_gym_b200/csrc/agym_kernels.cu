@@ -521,6 +521,8 @@ __global__ void __launch_bounds__(kIngestThreads, 3) k_ingest_atari_tma(const __
                                                                         int span_rows) {
     extern __shared__ __align__(16) uint8_t smem[];
     __shared__ __align__(8) uint64_t full[kStages], empty[kStages];
+    constexpr int kEnvWin = 64;
+    __shared__ int s_envfl[kEnvWin], s_envhd[kEnvWin];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int N = p.N, K = p.K;
     const int raw_w = RAW_W ? RAW_W : p.raw_w;
@@ -605,11 +607,22 @@ __global__ void __launch_bounds__(kIngestThreads, 3) k_ingest_atari_tma(const __
     const uint4 *sqq4 = reinterpret_cast<const uint4 *>(s_sqq) + 2 * sq_i;  // fixed-point weights of this column
 
     int slot = 0, fl = 0;
-    for (int it = 0, n = blockIdx.x, part = 0, st = 0, ph = 0; it < my_units; ++it) {
+    for (int it = 0, n = blockIdx.x, part = 0, st = 0, ph = 0, je = 0; it < my_units; ++it) {
         if (part == 0) {
-            fl = flags[n];
-            slot = head[n] + 1;
+            // flags / head of this CTA's next kEnvWin envs are fetched together into shared memory: a load per
+            // env, used at once, left every warp waiting ~a microsecond of DRAM latency per env
+            if ((je & (kEnvWin - 1)) == 0) {
+                consumer_sync();
+                if (tid < kEnvWin && (long long)n + (long long)tid * gridDim.x < N) {
+                    s_envfl[tid] = flags[n + tid * gridDim.x];
+                    s_envhd[tid] = head[n + tid * gridDim.x];
+                }
+                consumer_sync();
+            }
+            fl = s_envfl[je & (kEnvWin - 1)];
+            slot = s_envhd[je & (kEnvWin - 1)] + 1;
             slot -= slot >= K ? K : 0;
+            ++je;
         }
         const bool idle = fl & AGYM_FLAG_IDLE;
         mbar_wait(&full[st], ph);
