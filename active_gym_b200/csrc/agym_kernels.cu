@@ -703,9 +703,9 @@ __global__ void __launch_bounds__(kIngestThreads, 3) k_ingest_atari_tma(const __
             if (sq_rows && p.squeeze_q) {
                 // W pass in 16-bit fixed point: 8 IDP.2A over the aligned 16-byte window, exact integer sum
                 if (sq_worker) {
+                    const uint4 qa = sqq4[0], qb = sqq4[1];  // live only across this loop
                     for (int y = sq_y0; y < p.S_h; y += sq_rows) {
                         const uint32_t *src = reinterpret_cast<const uint32_t *>(s_frame + y * S_w + sq_o.x);
-                        const uint4 qa = sqq4[0], qb = sqq4[1];
                         uint32_t acc = __dp2a_lo(qa.x, src[0], 0u);
                         acc = __dp2a_hi(qa.y, src[0], acc);
                         acc = __dp2a_lo(qa.z, src[1], acc);
