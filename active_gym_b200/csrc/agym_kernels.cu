@@ -1362,7 +1362,13 @@ __global__ void __launch_bounds__(((StdGeom::Q * StdGeom::SEG * K + 31) / 32) * 
 
     const bool active = tid < NB;
     const int q = tid % Q, t2 = tid / Q;
-    const int g = active ? t2 % Gm::SEG : 0, k = active ? t2 / Gm::SEG : 0;
+    // which (frame, segment) group the t2-th run of 21 threads works on: an order found by search that keeps
+    // the two or three groups sharing a warp on different shared-memory banks when they store their tile words
+    // (word offset 1764 k + 441 g + 21 r + q); in k-major order every warp's stores were 2-way conflicts
+    constexpr int kOrd4[16] = {7, 4, 13, 3, 0, 1, 9, 6, 10, 14, 11, 12, 8, 5, 15, 2};
+    constexpr int kOrd3[12] = {11, 8, 5, 2, 9, 6, 3, 0, 10, 4, 1, 7};
+    const int grp = !active ? 0 : (K == 4 ? kOrd4[t2 & 15] : (K == 3 ? kOrd3[t2 % 12] : t2));
+    const int g = grp % Gm::SEG, k = grp / Gm::SEG;
     // W pass: samples base .. base + 2 of a squeezed row cover this quad's columns
     int base;
     uint64_t wa01, wa23, wb01, wb23, wc01, wc23;  // weights of s0 / s1 / s2 for columns (0,1) and (2,3)
