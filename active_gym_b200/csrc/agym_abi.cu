@@ -151,7 +151,8 @@ int agym_plan_create(const agym_config *cfg, agym_plan **out_plan) {
         ex_w = add_axis(pool, c.periph_w, c.obs_w); ex_h = add_axis(pool, c.periph_h, c.obs_h);
     }
     const int s_max = c.obs_h > c.obs_w ? c.obs_h : c.obs_w;
-    size_t o_flex = 0, o_flexb = 0;
+    size_t o_flex = 0, o_flexb = 0, o_flexq = 0;
+    bool have_flexq = false;
     int blur_tmax = 0;
     if (c.fov_h > 0) {
         full_w = add_axis(pool, c.fov_w, c.obs_w); full_h = add_axis(pool, c.fov_h, c.obs_h);
@@ -181,6 +182,41 @@ int agym_plan_create(const agym_config *cfg, agym_plan **out_plan) {
             }
         }
         o_flexb = pool.add_i(bindex);
+        // the W-axis operators once more in 16-bit fixed point for IDP.2A (k_observe_flexible_v3): per output
+        // column 8 weights per half (taps 0-7, 8-15) starting at xmin, scaled by 2^16 and rounded by largest
+        // remainder so that a row sums to 2^16 exactly (a lone weight of 1.0 is stored as 65535)
+        if (blur_tmax <= 16) {
+            std::vector<int32_t> qindex(static_cast<size_t>(s_max + 1) * 4, 0);
+            for (int r = 1; r <= c.obs_w; ++r) {
+                const AaAxis ax = build_blur_axis(r, c.fov_w);
+                const int nh = (ax.taps + 7) / 8;
+                std::vector<int32_t> q(static_cast<size_t>(r) * nh * 4, 0);
+                for (int x = 0; x < r; ++x) {
+                    int64_t v[16] = {0}, sum = 0;
+                    double frac[16] = {0};
+                    for (int t = 0; t < ax.taps; ++t) {
+                        const double w = static_cast<double>(ax.w[static_cast<size_t>(x) * ax.taps + t]) * 65536.0;
+                        v[t] = static_cast<int64_t>(std::floor(w));
+                        frac[t] = w - std::floor(w);
+                        sum += v[t];
+                    }
+                    for (int64_t left = 65536 - sum; left > 0; --left) {  // hand the missing units to the largest remainders
+                        int best = 0;
+                        for (int t = 1; t < ax.taps; ++t) if (frac[t] > frac[best]) best = t;
+                        if (frac[best] <= 0.0) break;
+                        ++v[best]; frac[best] = -1.0;
+                    }
+                    for (int t = 0; t < 16; ++t) v[t] = std::min<int64_t>(std::max<int64_t>(v[t], 0), 65535);
+                    for (int t = 0; t < nh * 8; t += 2)
+                        q[static_cast<size_t>(x) * nh * 4 + t / 2] = static_cast<int32_t>(static_cast<uint32_t>(v[t]) | (static_cast<uint32_t>(v[t + 1]) << 16));
+                }
+                int32_t *e = qindex.data() + static_cast<size_t>(r) * 4;
+                e[0] = static_cast<int32_t>(pool.add_i(ax.xmin)); e[1] = static_cast<int32_t>(pool.add_i(q));
+                e[2] = nh; e[3] = ax.taps;
+            }
+            o_flexq = pool.add_i(qindex);
+            have_flexq = true;
+        }
     }
 
     // ---- fast-path tables (see DevPlan)
@@ -320,6 +356,7 @@ int agym_plan_create(const agym_config *cfg, agym_plan **out_plan) {
         d.flex = reinterpret_cast<const FlexEntry *>(base + o_flex);
         d.flexb = reinterpret_cast<const FlexEntry *>(base + o_flexb);
         d.blur_tmax = blur_tmax;
+        d.flexq = have_flexq ? reinterpret_cast<const FlexEntry *>(base + o_flexq) : nullptr;
     }
     d.pool_i = reinterpret_cast<const int32_t *>(base);
     d.S_max = s_max;

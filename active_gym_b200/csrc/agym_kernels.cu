@@ -1766,6 +1766,252 @@ __global__ void __launch_bounds__(kThreads) k_observe_flexible_fast(const __grid
     }
 }
 
+// Persistent flexible fovea (mask_out in place, or the zero-padded crop): the successor of
+// k_observe_flexible_fast.  A few CTAs per SM walk the env batch and keep three things in flight:
+//   * warp 0 applies the sensory actions (fov_env.py:314-330) of this CTA's next 32 envs, one env per
+//     lane, a batch ahead of their use;
+//   * the K windows of env j+1 (and its W operator) travel by cp.async while env j is in its H pass;
+//   * the finished frame tile of env j leaves as one TMA bulk store while env j+1 is computed.
+// The blur Resize(fov_size) -> Resize(fov_res) (fov_env.py:276-280) is one banded operator per axis.
+// Along W it runs on the staged bytes in 16-bit fixed point: 8 taps = 4 IDP.2A on a funnel-shifted
+// 8-byte window, weights * 2^16 summing to 2^16 exactly (<= 255 * taps / 2^17 LSB from the fp64
+// weights: 0.01 LSB for the 5-tap operators of windows up to 50).  Along H it is fp32 on four columns
+// per thread; results are rounded to nearest-even with the 1.5 * 2^23 bias and leave as whole words.
+template <int TH>
+__device__ __forceinline__ float4 flex_hcol(const float *src, const float *w, int th, int rwp) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (TH > 0) {
+#pragma unroll
+        for (int t = 0; t < TH; ++t) {
+            const float4 v = *reinterpret_cast<const float4 *>(src + t * rwp);
+            const float wt = w[t];
+            acc.x = fmaf(wt, v.x, acc.x); acc.y = fmaf(wt, v.y, acc.y);
+            acc.z = fmaf(wt, v.z, acc.z); acc.w = fmaf(wt, v.w, acc.w);
+        }
+    } else {
+        for (int t = 0; t < th; ++t) {
+            const float4 v = *reinterpret_cast<const float4 *>(src + t * rwp);
+            const float wt = w[t];
+            acc.x = fmaf(wt, v.x, acc.x); acc.y = fmaf(wt, v.y, acc.y);
+            acc.z = fmaf(wt, v.z, acc.z); acc.w = fmaf(wt, v.w, acc.w);
+        }
+    }
+    return acc;
+}
+
+struct FlexGeom {
+    int rh, rwp, sb, vw, vh, nq, ow4, oy, wlo, oh;
+};
+
+// H pass over the frames [k0, k0 + kg): item = (frame row, output word)
+template <int TH>
+__device__ __forceinline__ void flex_hpass(const FlexGeom &g, const float *s_t1, const float *s_wh, const int32_t *s_xh,
+                                           uint32_t *s_tile, int k0, int kg, int th, int tid) {
+    const FastDiv fd_nq(g.nq), fd_rh(g.rh);
+    const int items = kg * g.rh * g.nq;
+    constexpr float kRne = 12582912.f;  // 1.5 * 2^23: v + kRne has rint(v) (half to even) in its low mantissa byte
+    for (int i = tid; i < items; i += kThreads) {
+        const int row = fd_nq.div(i), q = i - row * g.nq;
+        const int kk = fd_rh.div(row), y = row - kk * g.rh;
+        if (y >= g.vh) continue;
+        const float4 a = flex_hcol<TH>(s_t1 + (kk * g.rh + s_xh[y]) * g.rwp + 4 * q, s_wh + y * th, th, g.rwp);
+        const uint32_t b0 = __float_as_uint(a.x + kRne), b1 = __float_as_uint(a.y + kRne);
+        const uint32_t b2 = __float_as_uint(a.z + kRne), b3 = __float_as_uint(a.w + kRne);
+        const uint32_t word = __byte_perm(__byte_perm(b0, b1, 0x0040), __byte_perm(b2, b3, 0x0040), 0x5410);
+        s_tile[((k0 + kk) * g.oh + g.oy + y) * g.ow4 + g.wlo + q] = word & word_mask(4 * q, g.sb, g.sb + g.vw);
+    }
+}
+
+template <int VARIANT>
+__global__ void __launch_bounds__(kThreads, 2) k_observe_flexible_v3(const __grid_constant__ DevPlan p,
+                                                                     const uint8_t *__restrict__ ring,
+                                                                     const int32_t *__restrict__ head,
+                                                                     const double *__restrict__ action,
+                                                                     const int32_t *__restrict__ atype,
+                                                                     const uint8_t *__restrict__ ctrl,
+                                                                     int32_t *__restrict__ loc, int32_t *__restrict__ res,
+                                                                     int oh, int ow, int t1_cap, uint8_t *__restrict__ out) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    constexpr int kWin = 64;
+    __shared__ int s_er[kWin], s_ec[kWin], s_erh[kWin], s_erw[kWin], s_ehd[kWin];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int K = p.K, quads = p.S_w >> 2, xcap = quads + 3, plane4 = p.plane >> 2;
+    const int tile_bytes = K * oh * ow;
+    uint32_t *s_tile = reinterpret_cast<uint32_t *>(smem);                          // [K][oh][ow] bytes
+    uint32_t *s_x = s_tile + (tile_bytes >> 2);                                     // [K * rh][nwx + 2] window words
+    float *s_t1 = reinterpret_cast<float *>(smem + align16((size_t)tile_bytes + 4 * (size_t)K * p.S_h * xcap));  // [kg * rh][rwp]
+    uint32_t *s_wq = reinterpret_cast<uint32_t *>(s_t1 + t1_cap);                   // [rw][halves][4]; t1_cap % 4 == 0
+    float *s_wh = reinterpret_cast<float *>(s_wq + p.S_w * 8);                      // [rh][th]
+    int32_t *s_xw = reinterpret_cast<int32_t *>(s_wh + p.S_h * p.blur_tmax);        // [rw] first tap
+    int32_t *s_xh = s_xw + p.S_w;                                                   // [rh]
+    const int N = p.N, G = gridDim.x, bid = blockIdx.x;
+    const int my_envs = (N - bid + G - 1) / G;
+
+    // warp 0: fov_loc / fov_res of this CTA's envs j0 .. j0 + 31 (fov_env.py:314-330), one env per lane
+    auto env_batch = [&](int j0) {
+        const int j = j0 + lane;
+        if (j >= my_envs) return;
+        const int n = bid + j * G;
+        const int mode = ctrl ? ctrl[n] : AGYM_FOV_APPLY;
+        int r = loc[2 * n], c = loc[2 * n + 1], rh = res[2 * n], rw = res[2 * n + 1];
+        const int hd = head[n];
+        if (mode == AGYM_FOV_RESET) {
+            r = p.init_r; c = p.init_c; rh = p.f_h; rw = p.f_w;
+        } else if (mode == AGYM_FOV_APPLY) {
+            const double a0 = action[2 * n], a1 = action[2 * n + 1];
+            const int t = atype ? atype[n] : AGYM_ATYPE_FOV_LOC;
+            if (t == AGYM_ATYPE_FOV_RES) {  // fov_res = action, then re-clamp loc (fov_env.py:322-324)
+                rh = min(max((int)a0, 1), p.S_h);
+                rw = min(max((int)a1, 1), p.S_w);
+                r = clip_rint((double)r, 0.0, (double)(p.S_h - rh));
+                c = clip_rint((double)c, 0.0, (double)(p.S_w - rw));
+            } else {
+                double v0 = a0, v1 = a1;
+                if (p.relative) {
+                    v0 = (double)(r + clip_rint(a0, p.lo, p.hi));
+                    v1 = (double)(c + clip_rint(a1, p.lo, p.hi));
+                }
+                r = clip_rint(v0, 0.0, (double)(p.S_h - rh));
+                c = clip_rint(v1, 0.0, (double)(p.S_w - rw));
+            }
+        }
+        loc[2 * n] = r; loc[2 * n + 1] = c; res[2 * n] = rh; res[2 * n + 1] = rw;
+        const int e = j & (kWin - 1);
+        s_er[e] = r; s_ec[e] = c; s_erh[e] = rh; s_erw[e] = rw; s_ehd[e] = hd;
+    };
+    // all threads: the K windows of env j as aligned words, and its W operator, by cp.async (one group)
+    auto prefetch = [&](int j) {
+        if (j < my_envs) {
+            const int e = j & (kWin - 1), n = bid + j * G;
+            const int r0 = s_er[e], c0 = s_ec[e], rh = s_erh[e], rw = s_erw[e], h = s_ehd[e];
+            const int wq0 = c0 >> 2, nwx = ((c0 + rw - 1) >> 2) - wq0 + 1, nwxp = nwx + 2;
+            const uint32_t *src = reinterpret_cast<const uint32_t *>(ring) + (size_t)n * K * plane4 + r0 * quads + wq0;
+            const FastDiv fd_w(nwx), fd_h(rh);
+            for (int i = tid; i < K * rh * nwx; i += kThreads) {
+                const int row = fd_w.div(i), w = i - row * nwx;
+                const int k = fd_h.div(row), y = row - k * rh;
+                int slot = h + 1 + k;
+                slot -= slot >= K ? K : 0;
+                cp_async4(s_x + row * nwxp + w, src + slot * plane4 + y * quads + w);
+            }
+            if (rh > p.f_h) {
+                const FlexEntry ew = p.flexq[rw];
+                const int32_t *gq = p.pool_i + ew.w_off, *gx = p.pool_i + ew.xmin_off;
+                for (int i = tid; i < rw * ew.taps; i += kThreads) cp_async16(s_wq + 4 * i, gq + 4 * i);
+                for (int i = tid; i < rw; i += kThreads) cp_async4(s_xw + i, gx + i);
+            }
+        }
+        cp_async_commit();
+    };
+
+    if (warp == 0) env_batch(0);
+    __syncthreads();
+    prefetch(0);
+
+    for (int j = 0; j < my_envs; ++j) {
+        const int e = j & (kWin - 1), n = bid + j * G;
+        if ((j & 31) == 0 && warp == 0) env_batch(j + 32);
+        const int r0 = s_er[e], c0 = s_ec[e], rh = s_erh[e], rw = s_erw[e];
+        const bool blur = rh > p.f_h;  // row dimension only (fov_env.py:286)
+        const int oy = VARIANT == AGYM_OUT_MASK ? r0 : 0, ox = VARIANT == AGYM_OUT_MASK ? c0 : 0;
+        const int cb = c0 & 3, sb = ox & 3;
+        FlexGeom g;
+        g.rh = rh; g.sb = sb; g.oy = oy; g.oh = oh; g.ow4 = ow >> 2; g.wlo = ox >> 2;
+        g.vh = min(rh, oh - oy); g.vw = min(rw, ow - ox);
+        g.nq = ((sb + g.vw - 1) >> 2) + 1;
+        g.rwp = (sb + rw + 3) & ~3;
+        const int nwxp = ((c0 + rw - 1) >> 2) - (c0 >> 2) + 3;
+        int th = 1, nh = 1;
+        if (blur) {  // this env's H operator; s_wh / s_xh were last read before the previous env's final barrier
+            const FlexEntry eh = p.flexb[rh];
+            th = eh.taps;
+            nh = p.flexq[rw].taps;
+            const float *gh = reinterpret_cast<const float *>(p.pool_i + eh.w_off);
+            for (int i = tid; i < rh * th; i += kThreads) cp_async4(s_wh + i, gh + i);
+            for (int i = tid; i < rh; i += kThreads) cp_async4(s_xh + i, p.pool_i + eh.xmin_off + i);
+        }
+        cp_async_commit();
+        cp_async_wait<1>();                    // this thread's part of the windows (and W operator) has landed
+        if (tid == 0) bulk_wait_read<0>();     // the previous tile has been read by the TMA store
+        __syncthreads();                       // #1
+        {   // zero frame (everything outside the window stays zero)
+            const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
+            for (int i = tid; i < (tile_bytes >> 4); i += kThreads) reinterpret_cast<uint4 *>(s_tile)[i] = z4;
+        }
+        const int per = blur ? rh * g.rwp : rh * g.nq;
+        const int kg = min(K, t1_cap / per);
+        for (int k0 = 0; k0 < K; k0 += kg) {
+            const int kc = min(kg, K - k0);
+            const bool last = k0 + kc >= K;
+            if (k0) __syncthreads();           // the previous group's H pass has read t1
+            if (blur) {
+                // W pass: t1[row][sb + x] = 2^-16 * sum_t q[x][t] * X[row][xw[x] + t]
+                const FastDiv fd_rw(rw);
+                const int nrows = kc * rh, dx = kThreads % rw, dr = kThreads / rw;
+                int row = fd_rw.div(tid), x = tid - row * rw;
+                const uint32_t *xrow0 = s_x + k0 * rh * nwxp;
+                while (row < nrows) {
+                    const int b = cb + s_xw[x];
+                    const uint32_t sh = (uint32_t)(b & 3) * 8u;
+                    const uint32_t *sp = xrow0 + row * nwxp + (b >> 2);
+                    const uint4 *wq = reinterpret_cast<const uint4 *>(s_wq) + x * nh;
+                    uint32_t acc = 0u;
+                    for (int hh = 0; hh < nh; ++hh) {
+                        const uint32_t a0 = sp[2 * hh], a1 = sp[2 * hh + 1], a2 = sp[2 * hh + 2];
+                        const uint32_t lo = __funnelshift_r(a0, a1, sh), hi = __funnelshift_r(a1, a2, sh);
+                        const uint4 q = wq[hh];
+                        acc = __dp2a_lo(q.x, lo, acc);
+                        acc = __dp2a_hi(q.y, lo, acc);
+                        acc = __dp2a_lo(q.z, hi, acc);
+                        acc = __dp2a_hi(q.w, hi, acc);
+                    }
+                    s_t1[row * g.rwp + sb + x] = (float)acc * (1.f / 65536.f);
+                    x += dx; row += dr;
+                    if (x >= rw) { x -= rw; ++row; }
+                }
+            } else {
+                // the window itself, bit exact: output words (bytes outside the window masked to zero) parked in t1
+                const FastDiv fd_nq(g.nq);
+                const uint32_t sh = (uint32_t)(cb - sb) * 8u;
+                uint32_t *t1w = reinterpret_cast<uint32_t *>(s_t1);
+                for (int i = tid; i < kc * rh * g.nq; i += kThreads) {
+                    const int row = fd_nq.div(i), q = i - row * g.nq;
+                    const uint32_t *sp = s_x + (k0 * rh + row) * nwxp + q;
+                    t1w[i] = __funnelshift_r(sp[0], sp[1], sh) & word_mask(4 * q, sb, sb + g.vw);
+                }
+            }
+            if (last) cp_async_wait<0>();      // H operator
+            __syncthreads();                   // #2: t1 complete; after the last group s_x / s_wq / s_xw are free
+            if (last) prefetch(j + 1);
+            if (blur) {
+                switch (th) {
+                    case 3: flex_hpass<3>(g, s_t1, s_wh, s_xh, s_tile, k0, kc, th, tid); break;
+                    case 4: flex_hpass<4>(g, s_t1, s_wh, s_xh, s_tile, k0, kc, th, tid); break;
+                    case 5: flex_hpass<5>(g, s_t1, s_wh, s_xh, s_tile, k0, kc, th, tid); break;
+                    case 6: flex_hpass<6>(g, s_t1, s_wh, s_xh, s_tile, k0, kc, th, tid); break;
+                    default: flex_hpass<0>(g, s_t1, s_wh, s_xh, s_tile, k0, kc, th, tid); break;
+                }
+            } else {
+                const FastDiv fd_nq(g.nq), fd_rh(rh);
+                const uint32_t *t1w = reinterpret_cast<const uint32_t *>(s_t1);
+                for (int i = tid; i < kc * rh * g.nq; i += kThreads) {
+                    const int row = fd_nq.div(i), q = i - row * g.nq;
+                    const int kk = fd_rh.div(row), y = row - kk * rh;
+                    if (y < g.vh) s_tile[((k0 + kk) * oh + oy + y) * g.ow4 + g.wlo + q] = t1w[i];
+                }
+            }
+        }
+        fence_async_smem();
+        __syncthreads();                       // #3: tile complete
+        if (tid == 0) {
+            bulk_s2g(out + (size_t)n * tile_bytes, s_tile, (uint32_t)tile_bytes);
+            bulk_commit();
+        }
+    }
+    cp_async_wait<0>();
+    if (tid == 0) bulk_wait_read<0>();
+}
+
 // ---------------------------------------------------------------------------- normalise
 // The reference hands the agent float32(u) / 255 (atari_env.py:75, dmc_env.py:183).  Consumer-side
 // convenience: u8 observations -> normalised f32 (bit-identical to the reference's value: IEEE
@@ -1834,6 +2080,8 @@ size_t a16(size_t v) { return (v + 15) & ~size_t(15); }
 const bool g_disable_std = getenv("AGYM_NO_STD") != nullptr;
 // AGYM_NO_TMA=1 forces the non-persistent ingest kernel (A/B comparisons, debugging)
 const bool g_disable_tma = getenv("AGYM_NO_TMA") != nullptr;
+// AGYM_FLEX_OLD=1 forces the one-CTA-per-env flexible kernel (A/B comparisons)
+const bool g_flex_old = getenv("AGYM_FLEX_OLD") != nullptr;
 // AGYM_INGEST_UNITS=n: units (shared-memory stages) per env of the TMA ingest kernel (tuning)
 const int g_units = getenv("AGYM_INGEST_UNITS") ? atoi(getenv("AGYM_INGEST_UNITS")) : 0;
 
@@ -2004,6 +2252,33 @@ cudaError_t launch_observe_flexible(const DevPlan &p, const uint8_t *ring, const
                                     const int32_t *atype, const uint8_t *ctrl, int32_t *loc, int32_t *res, int variant,
                                     int pad_h, int pad_w, uint8_t *out, cudaStream_t st) {
     cudaError_t e;
+    if (variant != AGYM_OUT_RESIZE_FULL && p.flexb && p.flexq && !g_disable_std && !g_flex_old) {
+        // persistent kernel, 2 CTAs per SM: whatever the fixed buffers leave of ~113 KB goes to t1
+        const int oh = variant == AGYM_OUT_CROP ? pad_h : p.S_h, ow = variant == AGYM_OUT_CROP ? pad_w : p.S_w;
+        const size_t tile = (size_t)p.K * oh * ow;
+        const size_t fixed = a16(tile + 4 * (size_t)p.K * p.S_h * (p.S_w / 4 + 3)) +
+                             4 * ((size_t)p.S_w * 8 + (size_t)p.S_h * p.blur_tmax + p.S_w + p.S_h) + 16;
+        const size_t budget = 111 * 1024;  // + static shared memory + 1 KB reserved per CTA: two CTAs per SM
+        const size_t one = (size_t)p.S_h * (p.S_w + 4), all = (size_t)p.K * one;   // floats: one / all K frames of the largest window
+        const size_t room = budget > fixed ? ((budget - fixed) / 4) & ~size_t(3) : 0;
+        const size_t t1_cap = std::min(all, room);
+        if (tile % 16 == 0 && ow % 4 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 && t1_cap >= one &&
+            (size_t)p.K * p.f_h * (p.S_w / 4 + 1) <= t1_cap) {
+            const size_t fs = fixed + 4 * t1_cap;
+            int dev = 0, sms = 148;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            const int grid = std::min(p.N, 2 * sms);
+            if (variant == AGYM_OUT_CROP) {
+                if ((e = set_smem(k_observe_flexible_v3<AGYM_OUT_CROP>, fs)) != cudaSuccess) return e;
+                k_observe_flexible_v3<AGYM_OUT_CROP><<<grid, kThreads, fs, st>>>(p, ring, head, action, atype, ctrl, loc, res, oh, ow, (int)t1_cap, out);
+            } else {
+                if ((e = set_smem(k_observe_flexible_v3<AGYM_OUT_MASK>, fs)) != cudaSuccess) return e;
+                k_observe_flexible_v3<AGYM_OUT_MASK><<<grid, kThreads, fs, st>>>(p, ring, head, action, atype, ctrl, loc, res, oh, ow, (int)t1_cap, out);
+            }
+            return cudaGetLastError();
+        }
+    }
     if (variant != AGYM_OUT_RESIZE_FULL && p.flexb && !g_disable_std) {
         const int oh = variant == AGYM_OUT_CROP ? pad_h : p.S_h, ow = variant == AGYM_OUT_CROP ? pad_w : p.S_w;
         const size_t tile = (size_t)p.K * oh * ow;

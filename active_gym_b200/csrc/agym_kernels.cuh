@@ -38,6 +38,8 @@ struct DevPlan {
     // composed blur (Resize(f) then Resize(r)) per axis and window size r: [2][S_max+1]; blur_tmax = widest band
     const FlexEntry *flexb;
     int32_t blur_tmax;
+    // W-axis blur operators in 16-bit fixed point: [S_max+1] {xmin_off, wq_off, halves of 8 taps, taps}; null = n/a
+    const FlexEntry *flexq;
     const int32_t *pool_i;  // pool base viewed as int32
     int32_t S_max;
     // ---- fast paths (0 = geometry not eligible, use the generic kernels)
