@@ -151,7 +151,7 @@ int agym_plan_create(const agym_config *cfg, agym_plan **out_plan) {
         ex_w = add_axis(pool, c.periph_w, c.obs_w); ex_h = add_axis(pool, c.periph_h, c.obs_h);
     }
     const int s_max = c.obs_h > c.obs_w ? c.obs_h : c.obs_w;
-    size_t o_flex = 0, o_flexb = 0, o_flexq = 0;
+    size_t o_flex = 0, o_flexb = 0, o_flexq = 0, o_flexh2 = 0, o_counters = 0;
     bool have_flexq = false;
     int blur_tmax = 0;
     if (c.fov_h > 0) {
@@ -215,6 +215,19 @@ int agym_plan_create(const agym_config *cfg, agym_plan **out_plan) {
                 e[2] = nh; e[3] = ax.taps;
             }
             o_flexq = pool.add_i(qindex);
+            // H-axis operators with every weight stored twice ({w, w} is the FFMA2 operand), padded to 16 bytes
+            std::vector<int32_t> hindex(static_cast<size_t>(s_max + 1) * 4, 0);
+            for (int r = 1; r <= c.obs_h; ++r) {
+                const AaAxis ax = build_blur_axis(r, c.fov_h);
+                std::vector<float> w2;
+                for (float w : ax.w) { w2.push_back(w); w2.push_back(w); }
+                while (w2.size() % 4) w2.push_back(0.f);
+                int32_t *e = hindex.data() + static_cast<size_t>(r) * 4;
+                e[0] = static_cast<int32_t>(pool.add_i(ax.xmin)); e[1] = static_cast<int32_t>(pool.add_f(w2));
+                e[2] = ax.taps; e[3] = ax.n_out;
+            }
+            o_flexh2 = pool.add_i(hindex);
+            o_counters = pool.add_i(std::vector<int32_t>(4, 0));
             have_flexq = true;
         }
     }
@@ -357,6 +370,8 @@ int agym_plan_create(const agym_config *cfg, agym_plan **out_plan) {
         d.flexb = reinterpret_cast<const FlexEntry *>(base + o_flexb);
         d.blur_tmax = blur_tmax;
         d.flexq = have_flexq ? reinterpret_cast<const FlexEntry *>(base + o_flexq) : nullptr;
+        d.flexh2 = have_flexq ? reinterpret_cast<const FlexEntry *>(base + o_flexh2) : nullptr;
+        d.flex_counters = have_flexq ? reinterpret_cast<int32_t *>(static_cast<uint32_t *>(pl->pool) + o_counters) : nullptr;
     }
     d.pool_i = reinterpret_cast<const int32_t *>(base);
     d.S_max = s_max;

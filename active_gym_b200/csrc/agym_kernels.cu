@@ -1767,58 +1767,109 @@ __global__ void __launch_bounds__(kThreads) k_observe_flexible_fast(const __grid
 }
 
 // Persistent flexible fovea (mask_out in place, or the zero-padded crop): the successor of
-// k_observe_flexible_fast.  A few CTAs per SM walk the env batch and keep three things in flight:
-//   * warp 0 applies the sensory actions (fov_env.py:314-330) of this CTA's next 32 envs, one env per
-//     lane, a batch ahead of their use;
-//   * the K windows of env j+1 (and its W operator) travel by cp.async while env j is in its H pass;
-//   * the finished frame tile of env j leaves as one TMA bulk store while env j+1 is computed.
+// k_observe_flexible_fast.  Two CTAs per SM pull envs from a device counter (windows of 20..50 pixels,
+// blurred or not, make an env's cost vary 3x: a static split left a quarter of the SM time idle) and
+// keep three things in flight:
+//   * thread 0 claims the env two iterations ahead and applies its sensory action (fov_env.py:314-330):
+//     the atomic, the loads and the arithmetic are spread over the phases of the current env;
+//   * the K windows of the next env (and its W operator) travel by cp.async during the current H pass;
+//   * the finished frame tile leaves as one TMA bulk store while the next env is computed.
 // The blur Resize(fov_size) -> Resize(fov_res) (fov_env.py:276-280) is one banded operator per axis.
 // Along W it runs on the staged bytes in 16-bit fixed point: 8 taps = 4 IDP.2A on a funnel-shifted
-// 8-byte window, weights * 2^16 summing to 2^16 exactly (<= 255 * taps / 2^17 LSB from the fp64
-// weights: 0.01 LSB for the 5-tap operators of windows up to 50).  Along H it is fp32 on four columns
-// per thread; results are rounded to nearest-even with the 1.5 * 2^23 bias and leave as whole words.
-template <int TH>
-__device__ __forceinline__ float4 flex_hcol(const float *src, const float *w, int th, int rwp) {
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (TH > 0) {
-#pragma unroll
-        for (int t = 0; t < TH; ++t) {
-            const float4 v = *reinterpret_cast<const float4 *>(src + t * rwp);
-            const float wt = w[t];
-            acc.x = fmaf(wt, v.x, acc.x); acc.y = fmaf(wt, v.y, acc.y);
-            acc.z = fmaf(wt, v.z, acc.z); acc.w = fmaf(wt, v.w, acc.w);
-        }
-    } else {
-        for (int t = 0; t < th; ++t) {
-            const float4 v = *reinterpret_cast<const float4 *>(src + t * rwp);
-            const float wt = w[t];
-            acc.x = fmaf(wt, v.x, acc.x); acc.y = fmaf(wt, v.y, acc.y);
-            acc.z = fmaf(wt, v.z, acc.z); acc.w = fmaf(wt, v.w, acc.w);
-        }
-    }
-    return acc;
+// 8-byte window, two rows per thread, weights * 2^16 summing to 2^16 exactly (<= 255 * taps / 2^17 LSB
+// from the fp64 weights: 0.01 LSB for the 5-tap operators of windows up to 50).  Along H it is packed
+// fp32 (FFMA2) on four columns per thread; results are rounded to nearest-even with the 1.5 * 2^23 bias
+// and leave as whole words.
+__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
 }
 
 struct FlexGeom {
-    int rh, rwp, sb, vw, vh, nq, ow4, oy, wlo, oh;
+    int rh, rwp, vh, nq, ow4, oh, wlo, oy;
+    uint32_t m_first, m_last;  // byte masks of the first / last output word of a window row
 };
 
-// H pass over the frames [k0, k0 + kg): item = (frame row, output word)
+// H pass over kc frames: item = (frame row, output word); s_wh2 holds every weight twice (FFMA2 operand)
 template <int TH>
-__device__ __forceinline__ void flex_hpass(const FlexGeom &g, const float *s_t1, const float *s_wh, const int32_t *s_xh,
-                                           uint32_t *s_tile, int k0, int kg, int th, int tid) {
+__device__ __forceinline__ void flex_hpass(const FlexGeom &g, const float *s_t1, const uint64_t *s_wh2, const int32_t *s_xh,
+                                           uint32_t *s_tile, int k0, int kc, int th, int tid) {
     const FastDiv fd_nq(g.nq), fd_rh(g.rh);
-    const int items = kg * g.rh * g.nq;
-    constexpr float kRne = 12582912.f;  // 1.5 * 2^23: v + kRne has rint(v) (half to even) in its low mantissa byte
-    for (int i = tid; i < items; i += kThreads) {
-        const int row = fd_nq.div(i), q = i - row * g.nq;
+    const int nrows = kc * g.rh, dq = kThreads % g.nq, dr = kThreads / g.nq;
+    const uint64_t rne2 = pack2(12582912.f, 12582912.f);  // 1.5 * 2^23: v + bias has rint(v) (half to even) in its low byte
+    int row = fd_nq.div(tid), q = tid - row * g.nq;
+    while (row < nrows) {
         const int kk = fd_rh.div(row), y = row - kk * g.rh;
-        if (y >= g.vh) continue;
-        const float4 a = flex_hcol<TH>(s_t1 + (kk * g.rh + s_xh[y]) * g.rwp + 4 * q, s_wh + y * th, th, g.rwp);
-        const uint32_t b0 = __float_as_uint(a.x + kRne), b1 = __float_as_uint(a.y + kRne);
-        const uint32_t b2 = __float_as_uint(a.z + kRne), b3 = __float_as_uint(a.w + kRne);
-        const uint32_t word = __byte_perm(__byte_perm(b0, b1, 0x0040), __byte_perm(b2, b3, 0x0040), 0x5410);
-        s_tile[((k0 + kk) * g.oh + g.oy + y) * g.ow4 + g.wlo + q] = word & word_mask(4 * q, g.sb, g.sb + g.vw);
+        if (y < g.vh) {
+            const float *src = s_t1 + (kk * g.rh + s_xh[y]) * g.rwp + 4 * q;
+            const uint64_t *w = s_wh2 + y * th;
+            uint64_t a01 = 0ull, a23 = 0ull;
+            if (TH > 0) {
+#pragma unroll
+                for (int t = 0; t < TH; ++t) {
+                    const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(src + t * g.rwp);
+                    const uint64_t wt = w[t];
+                    a01 = ffma2(v.x, wt, a01);
+                    a23 = ffma2(v.y, wt, a23);
+                }
+            } else {
+                for (int t = 0; t < th; ++t) {
+                    const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(src + t * g.rwp);
+                    const uint64_t wt = w[t];
+                    a01 = ffma2(v.x, wt, a01);
+                    a23 = ffma2(v.y, wt, a23);
+                }
+            }
+            uint32_t b0, b1, b2, b3;
+            unpack2(fadd2(a01, rne2), b0, b1);
+            unpack2(fadd2(a23, rne2), b2, b3);
+            uint32_t word = __byte_perm(__byte_perm(b0, b1, 0x0040), __byte_perm(b2, b3, 0x0040), 0x5410);
+            if (q == 0) word &= g.m_first;
+            if (q == g.nq - 1) word &= g.m_last;
+            s_tile[((k0 + kk) * g.oh + g.oy + y) * g.ow4 + g.wlo + q] = word;
+        }
+        q += dq; row += dr;
+        if (q >= g.nq) { q -= g.nq; ++row; }
+    }
+}
+
+// W pass over nrows staged rows: t1[row][sb + x] = 2^-16 * sum_t q[x][t] * X[row][xw[x] + t]; a thread takes
+// column x of rows rp and rp + ceil(nrows / 2) (same weights and shift, two independent IDP.2A chains)
+template <int NH>
+__device__ __forceinline__ void flex_wpass(const uint32_t *xrow0, int nwxp, const int32_t *s_xw, const uint32_t *s_wq,
+                                           float *s_t1, int rwp, int sb, int cb, int rw, int nrows, int tid) {
+    const FastDiv fd_rw(rw);
+    const int nrp = (nrows + 1) >> 1, dx = kThreads % rw, dr = kThreads / rw;
+    int rp = fd_rw.div(tid), x = tid - rp * rw;
+    while (rp < nrp) {
+        const int b = cb + s_xw[x];
+        const uint32_t sh = (uint32_t)(b & 3) * 8u;
+        const uint32_t *sp0 = xrow0 + rp * nwxp + (b >> 2), *sp1 = sp0 + nrp * nwxp;
+        const bool two = rp + nrp < nrows;
+        const uint4 *wq = reinterpret_cast<const uint4 *>(s_wq) + x * NH;
+        uint32_t acc0 = 0u, acc1 = 0u;
+#pragma unroll
+        for (int hh = 0; hh < NH; ++hh) {
+            const uint4 q = wq[hh];
+            {
+                const uint32_t a0 = sp0[2 * hh], a1 = sp0[2 * hh + 1], a2 = sp0[2 * hh + 2];
+                const uint32_t lo = __funnelshift_r(a0, a1, sh), hi = __funnelshift_r(a1, a2, sh);
+                acc0 = __dp2a_lo(q.x, lo, acc0); acc0 = __dp2a_hi(q.y, lo, acc0);
+                acc0 = __dp2a_lo(q.z, hi, acc0); acc0 = __dp2a_hi(q.w, hi, acc0);
+            }
+            if (two) {
+                const uint32_t a0 = sp1[2 * hh], a1 = sp1[2 * hh + 1], a2 = sp1[2 * hh + 2];
+                const uint32_t lo = __funnelshift_r(a0, a1, sh), hi = __funnelshift_r(a1, a2, sh);
+                acc1 = __dp2a_lo(q.x, lo, acc1); acc1 = __dp2a_hi(q.y, lo, acc1);
+                acc1 = __dp2a_lo(q.z, hi, acc1); acc1 = __dp2a_hi(q.w, hi, acc1);
+            }
+        }
+        float *d = s_t1 + rp * rwp + sb + x;
+        d[0] = (float)acc0 * (1.f / 65536.f);
+        if (two) d[nrp * rwp] = (float)acc1 * (1.f / 65536.f);
+        x += dx; rp += dr;
+        if (x >= rw) { x -= rw; ++rp; }
     }
 }
 
@@ -1830,69 +1881,84 @@ __global__ void __launch_bounds__(kThreads, 2) k_observe_flexible_v3(const __gri
                                                                      const int32_t *__restrict__ atype,
                                                                      const uint8_t *__restrict__ ctrl,
                                                                      int32_t *__restrict__ loc, int32_t *__restrict__ res,
-                                                                     int oh, int ow, int t1_cap, uint8_t *__restrict__ out) {
+                                                                     int oh, int ow, int t1_cap, uint8_t *__restrict__ out,
+                                                                     int *__restrict__ counters) {
     extern __shared__ __align__(16) uint8_t smem[];
-    constexpr int kWin = 64;
-    __shared__ int s_er[kWin], s_ec[kWin], s_erh[kWin], s_erw[kWin], s_ehd[kWin];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int K = p.K, quads = p.S_w >> 2, xcap = quads + 3, plane4 = p.plane >> 2;
+    constexpr int kWin = 4;
+    __shared__ int s_en[kWin], s_er[kWin], s_ec[kWin], s_erh[kWin], s_erw[kWin], s_ehd[kWin];
+    const int tid = threadIdx.x;
+    const int K = p.K, quads = p.S_w >> 2, xcap = quads + 2, plane4 = p.plane >> 2;
     const int tile_bytes = K * oh * ow;
     uint32_t *s_tile = reinterpret_cast<uint32_t *>(smem);                          // [K][oh][ow] bytes
     uint32_t *s_x = s_tile + (tile_bytes >> 2);                                     // [K * rh][nwx + 2] window words
     float *s_t1 = reinterpret_cast<float *>(smem + align16((size_t)tile_bytes + 4 * (size_t)K * p.S_h * xcap));  // [kg * rh][rwp]
     uint32_t *s_wq = reinterpret_cast<uint32_t *>(s_t1 + t1_cap);                   // [rw][halves][4]; t1_cap % 4 == 0
-    float *s_wh = reinterpret_cast<float *>(s_wq + p.S_w * 8);                      // [rh][th]
-    int32_t *s_xw = reinterpret_cast<int32_t *>(s_wh + p.S_h * p.blur_tmax);        // [rw] first tap
+    uint64_t *s_wh2 = reinterpret_cast<uint64_t *>(s_wq + p.S_w * 8);               // [rh][th] {w, w}
+    int32_t *s_xw = reinterpret_cast<int32_t *>(s_wh2 + p.S_h * p.blur_tmax);       // [rw] first tap
     int32_t *s_xh = s_xw + p.S_w;                                                   // [rh]
-    const int N = p.N, G = gridDim.x, bid = blockIdx.x;
-    const int my_envs = (N - bid + G - 1) / G;
+    const int N = p.N;
 
-    // warp 0: fov_loc / fov_res of this CTA's envs j0 .. j0 + 31 (fov_env.py:314-330), one env per lane
-    auto env_batch = [&](int j0) {
-        const int j = j0 + lane;
-        if (j >= my_envs) return;
-        const int n = bid + j * G;
-        const int mode = ctrl ? ctrl[n] : AGYM_FOV_APPLY;
-        int r = loc[2 * n], c = loc[2 * n + 1], rh = res[2 * n], rw = res[2 * n + 1];
-        const int hd = head[n];
-        if (mode == AGYM_FOV_RESET) {
+    // ---- thread 0: claim an env, load what its fov update needs, apply it (three steps, spread over an iteration)
+    struct Pend { int n, mode, r, c, rh, rw, hd, t; double a0, a1; };
+    bool more = true;
+    auto claim = [&]() {
+        if (!more) return N;
+        const int n = atomicAdd(counters, 1);
+        more = n < N;
+        return more ? n : N;
+    };
+    auto load_env = [&](int n, Pend &q) {
+        q.n = n;
+        if (n >= N) return;
+        q.mode = ctrl ? ctrl[n] : AGYM_FOV_APPLY;
+        q.r = loc[2 * n]; q.c = loc[2 * n + 1]; q.rh = res[2 * n]; q.rw = res[2 * n + 1];
+        q.hd = head[n];
+        q.a0 = action ? action[2 * n] : 0.0; q.a1 = action ? action[2 * n + 1] : 0.0;
+        q.t = atype ? atype[n] : AGYM_ATYPE_FOV_LOC;
+    };
+    auto finish_env = [&](const Pend &q, int e) {
+        s_en[e] = q.n;
+        if (q.n >= N) return;
+        int r = q.r, c = q.c, rh = q.rh, rw = q.rw;
+        if (q.mode == AGYM_FOV_RESET) {
             r = p.init_r; c = p.init_c; rh = p.f_h; rw = p.f_w;
-        } else if (mode == AGYM_FOV_APPLY) {
-            const double a0 = action[2 * n], a1 = action[2 * n + 1];
-            const int t = atype ? atype[n] : AGYM_ATYPE_FOV_LOC;
-            if (t == AGYM_ATYPE_FOV_RES) {  // fov_res = action, then re-clamp loc (fov_env.py:322-324)
-                rh = min(max((int)a0, 1), p.S_h);
-                rw = min(max((int)a1, 1), p.S_w);
+        } else if (q.mode == AGYM_FOV_APPLY) {
+            if (q.t == AGYM_ATYPE_FOV_RES) {  // fov_res = action, then re-clamp loc (fov_env.py:322-324)
+                rh = min(max((int)q.a0, 1), p.S_h);
+                rw = min(max((int)q.a1, 1), p.S_w);
                 r = clip_rint((double)r, 0.0, (double)(p.S_h - rh));
                 c = clip_rint((double)c, 0.0, (double)(p.S_w - rw));
             } else {
-                double v0 = a0, v1 = a1;
+                double v0 = q.a0, v1 = q.a1;
                 if (p.relative) {
-                    v0 = (double)(r + clip_rint(a0, p.lo, p.hi));
-                    v1 = (double)(c + clip_rint(a1, p.lo, p.hi));
+                    v0 = (double)(r + clip_rint(q.a0, p.lo, p.hi));
+                    v1 = (double)(c + clip_rint(q.a1, p.lo, p.hi));
                 }
                 r = clip_rint(v0, 0.0, (double)(p.S_h - rh));
                 c = clip_rint(v1, 0.0, (double)(p.S_w - rw));
             }
         }
+        const int n = q.n;
         loc[2 * n] = r; loc[2 * n + 1] = c; res[2 * n] = rh; res[2 * n + 1] = rw;
-        const int e = j & (kWin - 1);
-        s_er[e] = r; s_ec[e] = c; s_erh[e] = rh; s_erw[e] = rw; s_ehd[e] = hd;
+        s_er[e] = r; s_ec[e] = c; s_erh[e] = rh; s_erw[e] = rw; s_ehd[e] = q.hd;
     };
-    // all threads: the K windows of env j as aligned words, and its W operator, by cp.async (one group)
-    auto prefetch = [&](int j) {
-        if (j < my_envs) {
-            const int e = j & (kWin - 1), n = bid + j * G;
+    // ---- all threads: the K windows of entry e as aligned words, and its W operator, by cp.async (one group)
+    auto prefetch = [&](int e) {
+        const int n = s_en[e];
+        if (n < N) {
             const int r0 = s_er[e], c0 = s_ec[e], rh = s_erh[e], rw = s_erw[e], h = s_ehd[e];
             const int wq0 = c0 >> 2, nwx = ((c0 + rw - 1) >> 2) - wq0 + 1, nwxp = nwx + 2;
             const uint32_t *src = reinterpret_cast<const uint32_t *>(ring) + (size_t)n * K * plane4 + r0 * quads + wq0;
             const FastDiv fd_w(nwx), fd_h(rh);
-            for (int i = tid; i < K * rh * nwx; i += kThreads) {
-                const int row = fd_w.div(i), w = i - row * nwx;
+            const int nrows = K * rh, dw = kThreads % nwx, dr = kThreads / nwx;
+            int row = fd_w.div(tid), w = tid - row * nwx;
+            while (row < nrows) {
                 const int k = fd_h.div(row), y = row - k * rh;
                 int slot = h + 1 + k;
                 slot -= slot >= K ? K : 0;
                 cp_async4(s_x + row * nwxp + w, src + slot * plane4 + y * quads + w);
+                w += dw; row += dr;
+                if (w >= nwx) { w -= nwx; ++row; }
             }
             if (rh > p.f_h) {
                 const FlexEntry ew = p.flexq[rw];
@@ -1904,30 +1970,41 @@ __global__ void __launch_bounds__(kThreads, 2) k_observe_flexible_v3(const __gri
         cp_async_commit();
     };
 
-    if (warp == 0) env_batch(0);
+    if (tid == 0) {
+        Pend q0, q1;
+        load_env(claim(), q0);
+        load_env(q0.n < N ? claim() : N, q1);
+        finish_env(q0, 0);
+        finish_env(q1, 1);
+    }
     __syncthreads();
     prefetch(0);
 
-    for (int j = 0; j < my_envs; ++j) {
-        const int e = j & (kWin - 1), n = bid + j * G;
-        if ((j & 31) == 0 && warp == 0) env_batch(j + 32);
+    for (int j = 0;; ++j) {
+        const int e = j & (kWin - 1), n = s_en[e];
+        if (n >= N) break;
+        int n2 = N;
+        if (tid == 0) n2 = claim();              // the env two iterations ahead; the result is not needed before #2
         const int r0 = s_er[e], c0 = s_ec[e], rh = s_erh[e], rw = s_erw[e];
         const bool blur = rh > p.f_h;  // row dimension only (fov_env.py:286)
         const int oy = VARIANT == AGYM_OUT_MASK ? r0 : 0, ox = VARIANT == AGYM_OUT_MASK ? c0 : 0;
         const int cb = c0 & 3, sb = ox & 3;
+        const int vw = min(rw, ow - ox);
         FlexGeom g;
-        g.rh = rh; g.sb = sb; g.oy = oy; g.oh = oh; g.ow4 = ow >> 2; g.wlo = ox >> 2;
-        g.vh = min(rh, oh - oy); g.vw = min(rw, ow - ox);
-        g.nq = ((sb + g.vw - 1) >> 2) + 1;
+        g.rh = rh; g.oy = oy; g.oh = oh; g.ow4 = ow >> 2; g.wlo = ox >> 2;
+        g.vh = min(rh, oh - oy);
+        g.nq = ((sb + vw - 1) >> 2) + 1;
         g.rwp = (sb + rw + 3) & ~3;
+        g.m_first = word_mask(0, sb, sb + vw);
+        g.m_last = word_mask(4 * (g.nq - 1), sb, sb + vw);
         const int nwxp = ((c0 + rw - 1) >> 2) - (c0 >> 2) + 3;
         int th = 1, nh = 1;
-        if (blur) {  // this env's H operator; s_wh / s_xh were last read before the previous env's final barrier
-            const FlexEntry eh = p.flexb[rh];
+        if (blur) {  // this env's H operator; s_wh2 / s_xh were last read before the previous env's final barrier
+            const FlexEntry eh = p.flexh2[rh];
             th = eh.taps;
             nh = p.flexq[rw].taps;
-            const float *gh = reinterpret_cast<const float *>(p.pool_i + eh.w_off);
-            for (int i = tid; i < rh * th; i += kThreads) cp_async4(s_wh + i, gh + i);
+            const int32_t *gh = p.pool_i + eh.w_off;
+            for (int i = tid; i < (rh * th + 1) >> 1; i += kThreads) cp_async16(s_wh2 + 2 * i, gh + 4 * i);
             for (int i = tid; i < rh; i += kThreads) cp_async4(s_xh + i, p.pool_i + eh.xmin_off + i);
         }
         cp_async_commit();
@@ -1940,35 +2017,15 @@ __global__ void __launch_bounds__(kThreads, 2) k_observe_flexible_v3(const __gri
         }
         const int per = blur ? rh * g.rwp : rh * g.nq;
         const int kg = min(K, t1_cap / per);
+        Pend pend;
+        pend.n = N;
         for (int k0 = 0; k0 < K; k0 += kg) {
             const int kc = min(kg, K - k0);
             const bool last = k0 + kc >= K;
             if (k0) __syncthreads();           // the previous group's H pass has read t1
             if (blur) {
-                // W pass: t1[row][sb + x] = 2^-16 * sum_t q[x][t] * X[row][xw[x] + t]
-                const FastDiv fd_rw(rw);
-                const int nrows = kc * rh, dx = kThreads % rw, dr = kThreads / rw;
-                int row = fd_rw.div(tid), x = tid - row * rw;
-                const uint32_t *xrow0 = s_x + k0 * rh * nwxp;
-                while (row < nrows) {
-                    const int b = cb + s_xw[x];
-                    const uint32_t sh = (uint32_t)(b & 3) * 8u;
-                    const uint32_t *sp = xrow0 + row * nwxp + (b >> 2);
-                    const uint4 *wq = reinterpret_cast<const uint4 *>(s_wq) + x * nh;
-                    uint32_t acc = 0u;
-                    for (int hh = 0; hh < nh; ++hh) {
-                        const uint32_t a0 = sp[2 * hh], a1 = sp[2 * hh + 1], a2 = sp[2 * hh + 2];
-                        const uint32_t lo = __funnelshift_r(a0, a1, sh), hi = __funnelshift_r(a1, a2, sh);
-                        const uint4 q = wq[hh];
-                        acc = __dp2a_lo(q.x, lo, acc);
-                        acc = __dp2a_hi(q.y, lo, acc);
-                        acc = __dp2a_lo(q.z, hi, acc);
-                        acc = __dp2a_hi(q.w, hi, acc);
-                    }
-                    s_t1[row * g.rwp + sb + x] = (float)acc * (1.f / 65536.f);
-                    x += dx; row += dr;
-                    if (x >= rw) { x -= rw; ++row; }
-                }
+                if (nh == 1) flex_wpass<1>(s_x + k0 * rh * nwxp, nwxp, s_xw, s_wq, s_t1, g.rwp, sb, cb, rw, kc * rh, tid);
+                else flex_wpass<2>(s_x + k0 * rh * nwxp, nwxp, s_xw, s_wq, s_t1, g.rwp, sb, cb, rw, kc * rh, tid);
             } else {
                 // the window itself, bit exact: output words (bytes outside the window masked to zero) parked in t1
                 const FastDiv fd_nq(g.nq);
@@ -1977,19 +2034,25 @@ __global__ void __launch_bounds__(kThreads, 2) k_observe_flexible_v3(const __gri
                 for (int i = tid; i < kc * rh * g.nq; i += kThreads) {
                     const int row = fd_nq.div(i), q = i - row * g.nq;
                     const uint32_t *sp = s_x + (k0 * rh + row) * nwxp + q;
-                    t1w[i] = __funnelshift_r(sp[0], sp[1], sh) & word_mask(4 * q, sb, sb + g.vw);
+                    uint32_t word = __funnelshift_r(sp[0], sp[1], sh);
+                    if (q == 0) word &= g.m_first;
+                    if (q == g.nq - 1) word &= g.m_last;
+                    t1w[i] = word;
                 }
             }
             if (last) cp_async_wait<0>();      // H operator
             __syncthreads();                   // #2: t1 complete; after the last group s_x / s_wq / s_xw are free
-            if (last) prefetch(j + 1);
+            if (last) {
+                prefetch((j + 1) & (kWin - 1));
+                if (tid == 0) load_env(n2, pend);
+            }
             if (blur) {
                 switch (th) {
-                    case 3: flex_hpass<3>(g, s_t1, s_wh, s_xh, s_tile, k0, kc, th, tid); break;
-                    case 4: flex_hpass<4>(g, s_t1, s_wh, s_xh, s_tile, k0, kc, th, tid); break;
-                    case 5: flex_hpass<5>(g, s_t1, s_wh, s_xh, s_tile, k0, kc, th, tid); break;
-                    case 6: flex_hpass<6>(g, s_t1, s_wh, s_xh, s_tile, k0, kc, th, tid); break;
-                    default: flex_hpass<0>(g, s_t1, s_wh, s_xh, s_tile, k0, kc, th, tid); break;
+                    case 3: flex_hpass<3>(g, s_t1, s_wh2, s_xh, s_tile, k0, kc, th, tid); break;
+                    case 4: flex_hpass<4>(g, s_t1, s_wh2, s_xh, s_tile, k0, kc, th, tid); break;
+                    case 5: flex_hpass<5>(g, s_t1, s_wh2, s_xh, s_tile, k0, kc, th, tid); break;
+                    case 6: flex_hpass<6>(g, s_t1, s_wh2, s_xh, s_tile, k0, kc, th, tid); break;
+                    default: flex_hpass<0>(g, s_t1, s_wh2, s_xh, s_tile, k0, kc, th, tid); break;
                 }
             } else {
                 const FastDiv fd_nq(g.nq), fd_rh(rh);
@@ -2006,10 +2069,19 @@ __global__ void __launch_bounds__(kThreads, 2) k_observe_flexible_v3(const __gri
         if (tid == 0) {
             bulk_s2g(out + (size_t)n * tile_bytes, s_tile, (uint32_t)tile_bytes);
             bulk_commit();
+            finish_env(pend, (j + 2) & (kWin - 1));
         }
     }
     cp_async_wait<0>();
-    if (tid == 0) bulk_wait_read<0>();
+    if (tid == 0) {
+        bulk_wait_read<0>();
+        // the last CTA to leave re-arms the counters for the next launch
+        __threadfence();
+        if (atomicAdd(counters + 1, 1) == (int)gridDim.x - 1) {
+            atomicExch(counters, 0);
+            atomicExch(counters + 1, 0);
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------- normalise
@@ -2256,9 +2328,9 @@ cudaError_t launch_observe_flexible(const DevPlan &p, const uint8_t *ring, const
         // persistent kernel, 2 CTAs per SM: whatever the fixed buffers leave of ~113 KB goes to t1
         const int oh = variant == AGYM_OUT_CROP ? pad_h : p.S_h, ow = variant == AGYM_OUT_CROP ? pad_w : p.S_w;
         const size_t tile = (size_t)p.K * oh * ow;
-        const size_t fixed = a16(tile + 4 * (size_t)p.K * p.S_h * (p.S_w / 4 + 3)) +
-                             4 * ((size_t)p.S_w * 8 + (size_t)p.S_h * p.blur_tmax + p.S_w + p.S_h) + 16;
-        const size_t budget = 111 * 1024;  // + static shared memory + 1 KB reserved per CTA: two CTAs per SM
+        const size_t fixed = a16(tile + 4 * (size_t)p.K * p.S_h * (p.S_w / 4 + 2)) +
+                             4 * ((size_t)p.S_w * 8 + 2 * (size_t)p.S_h * p.blur_tmax + p.S_w + p.S_h) + 16;
+        const size_t budget = 115000;  // + static shared memory + 1 KB reserved per CTA: two CTAs per SM (233,472 B)
         const size_t one = (size_t)p.S_h * (p.S_w + 4), all = (size_t)p.K * one;   // floats: one / all K frames of the largest window
         const size_t room = budget > fixed ? ((budget - fixed) / 4) & ~size_t(3) : 0;
         const size_t t1_cap = std::min(all, room);
@@ -2271,10 +2343,10 @@ cudaError_t launch_observe_flexible(const DevPlan &p, const uint8_t *ring, const
             const int grid = std::min(p.N, 2 * sms);
             if (variant == AGYM_OUT_CROP) {
                 if ((e = set_smem(k_observe_flexible_v3<AGYM_OUT_CROP>, fs)) != cudaSuccess) return e;
-                k_observe_flexible_v3<AGYM_OUT_CROP><<<grid, kThreads, fs, st>>>(p, ring, head, action, atype, ctrl, loc, res, oh, ow, (int)t1_cap, out);
+                k_observe_flexible_v3<AGYM_OUT_CROP><<<grid, kThreads, fs, st>>>(p, ring, head, action, atype, ctrl, loc, res, oh, ow, (int)t1_cap, out, p.flex_counters);
             } else {
                 if ((e = set_smem(k_observe_flexible_v3<AGYM_OUT_MASK>, fs)) != cudaSuccess) return e;
-                k_observe_flexible_v3<AGYM_OUT_MASK><<<grid, kThreads, fs, st>>>(p, ring, head, action, atype, ctrl, loc, res, oh, ow, (int)t1_cap, out);
+                k_observe_flexible_v3<AGYM_OUT_MASK><<<grid, kThreads, fs, st>>>(p, ring, head, action, atype, ctrl, loc, res, oh, ow, (int)t1_cap, out, p.flex_counters);
             }
             return cudaGetLastError();
         }

@@ -40,6 +40,11 @@ struct DevPlan {
     int32_t blur_tmax;
     // W-axis blur operators in 16-bit fixed point: [S_max+1] {xmin_off, wq_off, halves of 8 taps, taps}; null = n/a
     const FlexEntry *flexq;
+    // H-axis blur operators with duplicated weights {w, w}: [S_max+1] {xmin_off, w2_off, taps, n_out}
+    const FlexEntry *flexh2;
+    // {next env, CTAs done}: work counter of the persistent flexible kernel; zero between launches (the last CTA
+    // re-arms it), so a plan must not run agym_observe_flexible on two streams at once
+    int32_t *flex_counters;
     const int32_t *pool_i;  // pool base viewed as int32
     int32_t S_max;
     // ---- fast paths (0 = geometry not eligible, use the generic kernels)
