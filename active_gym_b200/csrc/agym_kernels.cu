@@ -1780,6 +1780,11 @@ __global__ void __launch_bounds__(kThreads) k_observe_flexible_fast(const __grid
 // from the fp64 weights: 0.01 LSB for the 5-tap operators of windows up to 50).  Along H it is packed
 // fp32 (FFMA2) on four columns per thread; results are rounded to nearest-even with the 1.5 * 2^23 bias
 // and leave as whole words.
+#ifndef AGYM_FLEX_THREADS
+#define AGYM_FLEX_THREADS 256
+#endif
+constexpr int kFlexThreads = AGYM_FLEX_THREADS;
+
 __device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
     uint64_t d;
     asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
@@ -1796,7 +1801,7 @@ template <int TH>
 __device__ __forceinline__ void flex_hpass(const FlexGeom &g, const float *s_t1, const uint64_t *s_wh2, const int32_t *s_xh,
                                            uint32_t *s_tile, int k0, int kc, int th, int tid) {
     const FastDiv fd_nq(g.nq), fd_rh(g.rh);
-    const int nrows = kc * g.rh, dq = kThreads % g.nq, dr = kThreads / g.nq;
+    const int nrows = kc * g.rh, dq = kFlexThreads % g.nq, dr = kFlexThreads / g.nq;
     const uint64_t rne2 = pack2(12582912.f, 12582912.f);  // 1.5 * 2^23: v + bias has rint(v) (half to even) in its low byte
     int row = fd_nq.div(tid), q = tid - row * g.nq;
     while (row < nrows) {
@@ -1840,7 +1845,7 @@ template <int NH>
 __device__ __forceinline__ void flex_wpass(const uint32_t *xrow0, int nwxp, const int32_t *s_xw, const uint32_t *s_wq,
                                            float *s_t1, int rwp, int sb, int cb, int rw, int nrows, int tid) {
     const FastDiv fd_rw(rw);
-    const int nrp = (nrows + 1) >> 1, dx = kThreads % rw, dr = kThreads / rw;
+    const int nrp = (nrows + 1) >> 1, dx = kFlexThreads % rw, dr = kFlexThreads / rw;
     int rp = fd_rw.div(tid), x = tid - rp * rw;
     while (rp < nrp) {
         const int b = cb + s_xw[x];
@@ -1874,19 +1879,23 @@ __device__ __forceinline__ void flex_wpass(const uint32_t *xrow0, int nwxp, cons
 }
 
 template <int VARIANT>
-__global__ void __launch_bounds__(kThreads, 2) k_observe_flexible_v3(const __grid_constant__ DevPlan p,
-                                                                     const uint8_t *__restrict__ ring,
-                                                                     const int32_t *__restrict__ head,
-                                                                     const double *__restrict__ action,
-                                                                     const int32_t *__restrict__ atype,
-                                                                     const uint8_t *__restrict__ ctrl,
-                                                                     int32_t *__restrict__ loc, int32_t *__restrict__ res,
-                                                                     int oh, int ow, int t1_cap, uint8_t *__restrict__ out,
-                                                                     int *__restrict__ counters) {
+__global__ void __launch_bounds__(kFlexThreads + 32, 2) k_observe_flexible_v3(const __grid_constant__ DevPlan p,
+                                                                          const uint8_t *__restrict__ ring,
+                                                                          const int32_t *__restrict__ head,
+                                                                          const double *__restrict__ action,
+                                                                          const int32_t *__restrict__ atype,
+                                                                          const uint8_t *__restrict__ ctrl,
+                                                                          int32_t *__restrict__ loc, int32_t *__restrict__ res,
+                                                                          int oh, int ow, int t1_cap, uint8_t *__restrict__ out,
+                                                                          int *__restrict__ counters) {
     extern __shared__ __align__(16) uint8_t smem[];
     constexpr int kWin = 4;
+    // per claimed env: index, window, ring head, and where its operators live in the pool
     __shared__ int s_en[kWin], s_er[kWin], s_ec[kWin], s_erh[kWin], s_erw[kWin], s_ehd[kWin];
+    __shared__ int s_eth[kWin], s_ehw[kWin], s_ehx[kWin], s_enh[kWin], s_eqw[kWin], s_eqx[kWin];
     const int tid = threadIdx.x;
+    const bool worker = tid < kFlexThreads;        // warps 0 .. 7/11 compute, the last warp is the control warp
+    const bool boss = tid == kFlexThreads;         // its lane 0: env claims, fov updates, TMA stores
     const int K = p.K, quads = p.S_w >> 2, xcap = quads + 2, plane4 = p.plane >> 2;
     const int tile_bytes = K * oh * ow;
     uint32_t *s_tile = reinterpret_cast<uint32_t *>(smem);                          // [K][oh][ow] bytes
@@ -1898,7 +1907,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_observe_flexible_v3(const __gri
     int32_t *s_xh = s_xw + p.S_w;                                                   // [rh]
     const int N = p.N;
 
-    // ---- thread 0: claim an env, load what its fov update needs, apply it (three steps, spread over an iteration)
+    // ---- boss: claim an env, load what its fov update needs, apply it (three steps, spread over an iteration)
     struct Pend { int n, mode, r, c, rh, rw, hd, t; double a0, a1; };
     bool more = true;
     auto claim = [&]() {
@@ -1941,8 +1950,13 @@ __global__ void __launch_bounds__(kThreads, 2) k_observe_flexible_v3(const __gri
         const int n = q.n;
         loc[2 * n] = r; loc[2 * n + 1] = c; res[2 * n] = rh; res[2 * n + 1] = rw;
         s_er[e] = r; s_ec[e] = c; s_erh[e] = rh; s_erw[e] = rw; s_ehd[e] = q.hd;
+        if (rh > p.f_h) {
+            const FlexEntry eh = p.flexh2[rh], ew = p.flexq[rw];
+            s_eth[e] = eh.taps; s_ehw[e] = eh.w_off; s_ehx[e] = eh.xmin_off;
+            s_enh[e] = ew.taps; s_eqw[e] = ew.w_off; s_eqx[e] = ew.xmin_off;
+        }
     };
-    // ---- all threads: the K windows of entry e as aligned words, and its W operator, by cp.async (one group)
+    // ---- workers: the K windows of entry e as aligned words, and its W operator, by cp.async (one group)
     auto prefetch = [&](int e) {
         const int n = s_en[e];
         if (n < N) {
@@ -1950,7 +1964,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_observe_flexible_v3(const __gri
             const int wq0 = c0 >> 2, nwx = ((c0 + rw - 1) >> 2) - wq0 + 1, nwxp = nwx + 2;
             const uint32_t *src = reinterpret_cast<const uint32_t *>(ring) + (size_t)n * K * plane4 + r0 * quads + wq0;
             const FastDiv fd_w(nwx), fd_h(rh);
-            const int nrows = K * rh, dw = kThreads % nwx, dr = kThreads / nwx;
+            const int nrows = K * rh, dw = kFlexThreads % nwx, dr = kFlexThreads / nwx;
             int row = fd_w.div(tid), w = tid - row * nwx;
             while (row < nrows) {
                 const int k = fd_h.div(row), y = row - k * rh;
@@ -1961,16 +1975,15 @@ __global__ void __launch_bounds__(kThreads, 2) k_observe_flexible_v3(const __gri
                 if (w >= nwx) { w -= nwx; ++row; }
             }
             if (rh > p.f_h) {
-                const FlexEntry ew = p.flexq[rw];
-                const int32_t *gq = p.pool_i + ew.w_off, *gx = p.pool_i + ew.xmin_off;
-                for (int i = tid; i < rw * ew.taps; i += kThreads) cp_async16(s_wq + 4 * i, gq + 4 * i);
-                for (int i = tid; i < rw; i += kThreads) cp_async4(s_xw + i, gx + i);
+                const int32_t *gq = p.pool_i + s_eqw[e], *gx = p.pool_i + s_eqx[e];
+                for (int i = tid; i < rw * s_enh[e]; i += kFlexThreads) cp_async16(s_wq + 4 * i, gq + 4 * i);
+                for (int i = tid; i < rw; i += kFlexThreads) cp_async4(s_xw + i, gx + i);
             }
         }
         cp_async_commit();
     };
 
-    if (tid == 0) {
+    if (boss) {
         Pend q0, q1;
         load_env(claim(), q0);
         load_env(q0.n < N ? claim() : N, q1);
@@ -1978,13 +1991,13 @@ __global__ void __launch_bounds__(kThreads, 2) k_observe_flexible_v3(const __gri
         finish_env(q1, 1);
     }
     __syncthreads();
-    prefetch(0);
+    if (worker) prefetch(0);
 
     for (int j = 0;; ++j) {
         const int e = j & (kWin - 1), n = s_en[e];
         if (n >= N) break;
         int n2 = N;
-        if (tid == 0) n2 = claim();              // the env two iterations ahead; the result is not needed before #2
+        if (boss) n2 = claim();                  // the env two iterations ahead; the result is not needed before #1
         const int r0 = s_er[e], c0 = s_ec[e], rh = s_erh[e], rw = s_erw[e];
         const bool blur = rh > p.f_h;  // row dimension only (fov_env.py:286)
         const int oy = VARIANT == AGYM_OUT_MASK ? r0 : 0, ox = VARIANT == AGYM_OUT_MASK ? c0 : 0;
@@ -2000,30 +2013,33 @@ __global__ void __launch_bounds__(kThreads, 2) k_observe_flexible_v3(const __gri
         const int nwxp = ((c0 + rw - 1) >> 2) - (c0 >> 2) + 3;
         int th = 1, nh = 1;
         if (blur) {  // this env's H operator; s_wh2 / s_xh were last read before the previous env's final barrier
-            const FlexEntry eh = p.flexh2[rh];
-            th = eh.taps;
-            nh = p.flexq[rw].taps;
-            const int32_t *gh = p.pool_i + eh.w_off;
-            for (int i = tid; i < (rh * th + 1) >> 1; i += kThreads) cp_async16(s_wh2 + 2 * i, gh + 4 * i);
-            for (int i = tid; i < rh; i += kThreads) cp_async4(s_xh + i, p.pool_i + eh.xmin_off + i);
+            th = s_eth[e];
+            nh = s_enh[e];
+            if (worker) {
+                const int32_t *gh = p.pool_i + s_ehw[e], *gx = p.pool_i + s_ehx[e];
+                for (int i = tid; i < (rh * th + 1) >> 1; i += kFlexThreads) cp_async16(s_wh2 + 2 * i, gh + 4 * i);
+                for (int i = tid; i < rh; i += kFlexThreads) cp_async4(s_xh + i, gx + i);
+            }
         }
         cp_async_commit();
         cp_async_wait<1>();                    // this thread's part of the windows (and W operator) has landed
-        if (tid == 0) bulk_wait_read<0>();     // the previous tile has been read by the TMA store
+        if (boss) bulk_wait_read<0>();         // the previous tile has been read by the TMA store
         __syncthreads();                       // #1
-        {   // zero frame (everything outside the window stays zero)
+        Pend pend;
+        pend.n = N;
+        if (boss) load_env(n2, pend);
+        if (worker) {   // zero frame (everything outside the window stays zero)
             const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
-            for (int i = tid; i < (tile_bytes >> 4); i += kThreads) reinterpret_cast<uint4 *>(s_tile)[i] = z4;
+            for (int i = tid; i < (tile_bytes >> 4); i += kFlexThreads) reinterpret_cast<uint4 *>(s_tile)[i] = z4;
         }
         const int per = blur ? rh * g.rwp : rh * g.nq;
         const int kg = min(K, t1_cap / per);
-        Pend pend;
-        pend.n = N;
         for (int k0 = 0; k0 < K; k0 += kg) {
             const int kc = min(kg, K - k0);
             const bool last = k0 + kc >= K;
             if (k0) __syncthreads();           // the previous group's H pass has read t1
-            if (blur) {
+            if (!worker) {
+            } else if (blur) {
                 if (nh == 1) flex_wpass<1>(s_x + k0 * rh * nwxp, nwxp, s_xw, s_wq, s_t1, g.rwp, sb, cb, rw, kc * rh, tid);
                 else flex_wpass<2>(s_x + k0 * rh * nwxp, nwxp, s_xw, s_wq, s_t1, g.rwp, sb, cb, rw, kc * rh, tid);
             } else {
@@ -2031,7 +2047,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_observe_flexible_v3(const __gri
                 const FastDiv fd_nq(g.nq);
                 const uint32_t sh = (uint32_t)(cb - sb) * 8u;
                 uint32_t *t1w = reinterpret_cast<uint32_t *>(s_t1);
-                for (int i = tid; i < kc * rh * g.nq; i += kThreads) {
+                for (int i = tid; i < kc * rh * g.nq; i += kFlexThreads) {
                     const int row = fd_nq.div(i), q = i - row * g.nq;
                     const uint32_t *sp = s_x + (k0 * rh + row) * nwxp + q;
                     uint32_t word = __funnelshift_r(sp[0], sp[1], sh);
@@ -2042,10 +2058,9 @@ __global__ void __launch_bounds__(kThreads, 2) k_observe_flexible_v3(const __gri
             }
             if (last) cp_async_wait<0>();      // H operator
             __syncthreads();                   // #2: t1 complete; after the last group s_x / s_wq / s_xw are free
-            if (last) {
-                prefetch((j + 1) & (kWin - 1));
-                if (tid == 0) load_env(n2, pend);
-            }
+            if (last && boss) finish_env(pend, (j + 2) & (kWin - 1));  // read by the prefetch after the NEXT env's #2
+            if (!worker) continue;
+            if (last) prefetch((j + 1) & (kWin - 1));
             if (blur) {
                 switch (th) {
                     case 3: flex_hpass<3>(g, s_t1, s_wh2, s_xh, s_tile, k0, kc, th, tid); break;
@@ -2057,7 +2072,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_observe_flexible_v3(const __gri
             } else {
                 const FastDiv fd_nq(g.nq), fd_rh(rh);
                 const uint32_t *t1w = reinterpret_cast<const uint32_t *>(s_t1);
-                for (int i = tid; i < kc * rh * g.nq; i += kThreads) {
+                for (int i = tid; i < kc * rh * g.nq; i += kFlexThreads) {
                     const int row = fd_nq.div(i), q = i - row * g.nq;
                     const int kk = fd_rh.div(row), y = row - kk * rh;
                     if (y < g.vh) s_tile[((k0 + kk) * oh + oy + y) * g.ow4 + g.wlo + q] = t1w[i];
@@ -2066,14 +2081,13 @@ __global__ void __launch_bounds__(kThreads, 2) k_observe_flexible_v3(const __gri
         }
         fence_async_smem();
         __syncthreads();                       // #3: tile complete
-        if (tid == 0) {
+        if (boss) {
             bulk_s2g(out + (size_t)n * tile_bytes, s_tile, (uint32_t)tile_bytes);
             bulk_commit();
-            finish_env(pend, (j + 2) & (kWin - 1));
         }
     }
     cp_async_wait<0>();
-    if (tid == 0) {
+    if (boss) {
         bulk_wait_read<0>();
         // the last CTA to leave re-arms the counters for the next launch
         __threadfence();
@@ -2343,10 +2357,10 @@ cudaError_t launch_observe_flexible(const DevPlan &p, const uint8_t *ring, const
             const int grid = std::min(p.N, 2 * sms);
             if (variant == AGYM_OUT_CROP) {
                 if ((e = set_smem(k_observe_flexible_v3<AGYM_OUT_CROP>, fs)) != cudaSuccess) return e;
-                k_observe_flexible_v3<AGYM_OUT_CROP><<<grid, kThreads, fs, st>>>(p, ring, head, action, atype, ctrl, loc, res, oh, ow, (int)t1_cap, out, p.flex_counters);
+                k_observe_flexible_v3<AGYM_OUT_CROP><<<grid, kFlexThreads + 32, fs, st>>>(p, ring, head, action, atype, ctrl, loc, res, oh, ow, (int)t1_cap, out, p.flex_counters);
             } else {
                 if ((e = set_smem(k_observe_flexible_v3<AGYM_OUT_MASK>, fs)) != cudaSuccess) return e;
-                k_observe_flexible_v3<AGYM_OUT_MASK><<<grid, kThreads, fs, st>>>(p, ring, head, action, atype, ctrl, loc, res, oh, ow, (int)t1_cap, out, p.flex_counters);
+                k_observe_flexible_v3<AGYM_OUT_MASK><<<grid, kFlexThreads + 32, fs, st>>>(p, ring, head, action, atype, ctrl, loc, res, oh, ow, (int)t1_cap, out, p.flex_counters);
             }
             return cudaGetLastError();
         }

@@ -107,10 +107,13 @@ def test_peripheral_std_kernel_other_fovea_sizes():
         assert np.abs(got - orc.observe_peripheral(ring, head, loc, fov, (20, 20))).max() <= TOL, fov
 
 
-@pytest.mark.parametrize("variant,pad", [("mask", None), ("crop", None), ("crop", (52, 56))])
-def test_flexible_fast_path_many_envs(variant, pad):
+@pytest.mark.parametrize("variant,pad,n", [("mask", None, 300), ("crop", None, 300), ("crop", (52, 56), 300),
+                                           ("mask", None, 1500), ("crop", (52, 56), 1500)])
+def test_flexible_fast_path_many_envs(variant, pad, n):
+    # n = 1500: every persistent CTA (2 per SM) claims ~5 envs from the device counter, so the cp.async window
+    # prefetch, the two-ahead fov update and the re-armed counter (several launches) are all exercised
     rng = np.random.default_rng(21)
-    n, K, fov = 300, 4, (30, 30)
+    K, fov = 4, (30, 30)
     p = _path(n, K, fov_size=fov, sensory_action_mode="relative", sensory_action_space=(-10.0, 10.0))
     ring, head = orc.new_state(n, K, S)
     for step in range(K + 1):
