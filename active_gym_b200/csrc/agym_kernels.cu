@@ -39,6 +39,8 @@ struct FastDiv {
     uint32_t magic;
     int32_t d;
     __device__ __forceinline__ explicit FastDiv(int32_t dd) : magic(0xFFFFFFFFu / (uint32_t)dd + 1u), d(dd) {}
+    // multiplier from a table of 0xFFFFFFFF / d + 1 (d < 256) instead of an integer division
+    __device__ __forceinline__ FastDiv(int32_t dd, const uint32_t *table) : magic(table[dd]), d(dd) {}
     // exact for n * d < 2^32 (all indices here are < 2^24, divisors < 2^8)
     __device__ __forceinline__ int32_t div(int32_t n) const { return d == 1 ? n : (int32_t)__umulhi((uint32_t)n, magic); }
 };
@@ -1799,9 +1801,9 @@ struct FlexGeom {
 // H pass over kc frames: item = (frame row, output word); s_wh2 holds every weight twice (FFMA2 operand)
 template <int TH>
 __device__ __forceinline__ void flex_hpass(const FlexGeom &g, const float *s_t1, const uint64_t *s_wh2, const int32_t *s_xh,
-                                           uint32_t *s_tile, int k0, int kc, int th, int tid) {
-    const FastDiv fd_nq(g.nq), fd_rh(g.rh);
-    const int nrows = kc * g.rh, dq = kFlexThreads % g.nq, dr = kFlexThreads / g.nq;
+                                           uint32_t *s_tile, int k0, int kc, int th, int tid, const uint32_t *s_magic) {
+    const FastDiv fd_nq(g.nq, s_magic), fd_rh(g.rh, s_magic);
+    const int nrows = kc * g.rh, dr = fd_nq.div(kFlexThreads), dq = kFlexThreads - dr * g.nq;
     const uint64_t rne2 = pack2(12582912.f, 12582912.f);  // 1.5 * 2^23: v + bias has rint(v) (half to even) in its low byte
     int row = fd_nq.div(tid), q = tid - row * g.nq;
     while (row < nrows) {
@@ -1843,9 +1845,9 @@ __device__ __forceinline__ void flex_hpass(const FlexGeom &g, const float *s_t1,
 // column x of rows rp and rp + ceil(nrows / 2) (same weights and shift, two independent IDP.2A chains)
 template <int NH>
 __device__ __forceinline__ void flex_wpass(const uint32_t *xrow0, int nwxp, const int32_t *s_xw, const uint32_t *s_wq,
-                                           float *s_t1, int rwp, int sb, int cb, int rw, int nrows, int tid) {
-    const FastDiv fd_rw(rw);
-    const int nrp = (nrows + 1) >> 1, dx = kFlexThreads % rw, dr = kFlexThreads / rw;
+                                           float *s_t1, int rwp, int sb, int cb, int rw, int nrows, int tid, const uint32_t *s_magic) {
+    const FastDiv fd_rw(rw, s_magic);
+    const int nrp = (nrows + 1) >> 1, dr = fd_rw.div(kFlexThreads), dx = kFlexThreads - dr * rw;
     int rp = fd_rw.div(tid), x = tid - rp * rw;
     while (rp < nrp) {
         const int b = cb + s_xw[x];
@@ -1893,7 +1895,9 @@ __global__ void __launch_bounds__(kFlexThreads + 32, 2) k_observe_flexible_v3(co
     // per claimed env: index, window, ring head, and where its operators live in the pool
     __shared__ int s_en[kWin], s_er[kWin], s_ec[kWin], s_erh[kWin], s_erw[kWin], s_ehd[kWin];
     __shared__ int s_eth[kWin], s_ehw[kWin], s_ehx[kWin], s_enh[kWin], s_eqw[kWin], s_eqx[kWin];
+    __shared__ uint32_t s_magic[256];              // FastDiv multipliers of 1..255: a division per divisor and env otherwise
     const int tid = threadIdx.x;
+    if (tid < 256) s_magic[tid] = tid ? 0xFFFFFFFFu / (uint32_t)tid + 1u : 0u;
     const bool worker = tid < kFlexThreads;        // warps 0 .. 7/11 compute, the last warp is the control warp
     const bool boss = tid == kFlexThreads;         // its lane 0: env claims, fov updates, TMA stores
     const int K = p.K, quads = p.S_w >> 2, xcap = quads + 2, plane4 = p.plane >> 2;
@@ -1909,13 +1913,11 @@ __global__ void __launch_bounds__(kFlexThreads + 32, 2) k_observe_flexible_v3(co
 
     // ---- boss: claim an env, load what its fov update needs, apply it (three steps, spread over an iteration)
     struct Pend { int n, mode, r, c, rh, rw, hd, t; double a0, a1; };
+    // envs blockIdx.x and blockIdx.x + G are this CTA's without asking; the counter hands out the rest.  A claim
+    // is only issued here: its value is looked at a barrier later, so nobody waits for the atomic's round trip
     bool more = true;
-    auto claim = [&]() {
-        if (!more) return N;
-        const int n = atomicAdd(counters, 1);
-        more = n < N;
-        return more ? n : N;
-    };
+    const int n_static = 2 * (int)gridDim.x;
+    auto claim = [&]() { return more ? n_static + atomicAdd(counters, 1) : N; };
     auto load_env = [&](int n, Pend &q) {
         q.n = n;
         if (n >= N) return;
@@ -1963,8 +1965,8 @@ __global__ void __launch_bounds__(kFlexThreads + 32, 2) k_observe_flexible_v3(co
             const int r0 = s_er[e], c0 = s_ec[e], rh = s_erh[e], rw = s_erw[e], h = s_ehd[e];
             const int wq0 = c0 >> 2, nwx = ((c0 + rw - 1) >> 2) - wq0 + 1, nwxp = nwx + 2;
             const uint32_t *src = reinterpret_cast<const uint32_t *>(ring) + (size_t)n * K * plane4 + r0 * quads + wq0;
-            const FastDiv fd_w(nwx), fd_h(rh);
-            const int nrows = K * rh, dw = kFlexThreads % nwx, dr = kFlexThreads / nwx;
+            const FastDiv fd_w(nwx, s_magic), fd_h(rh, s_magic);
+            const int nrows = K * rh, dr = fd_w.div(kFlexThreads), dw = kFlexThreads - dr * nwx;
             int row = fd_w.div(tid), w = tid - row * nwx;
             while (row < nrows) {
                 const int k = fd_h.div(row), y = row - k * rh;
@@ -1985,10 +1987,11 @@ __global__ void __launch_bounds__(kFlexThreads + 32, 2) k_observe_flexible_v3(co
 
     if (boss) {
         Pend q0, q1;
-        load_env(claim(), q0);
-        load_env(q0.n < N ? claim() : N, q1);
+        load_env(min((int)blockIdx.x, N), q0);
+        load_env(min((int)(blockIdx.x + gridDim.x), N), q1);
         finish_env(q0, 0);
         finish_env(q1, 1);
+        more = q1.n < N;
     }
     __syncthreads();
     if (worker) prefetch(0);
@@ -2027,7 +2030,10 @@ __global__ void __launch_bounds__(kFlexThreads + 32, 2) k_observe_flexible_v3(co
         __syncthreads();                       // #1
         Pend pend;
         pend.n = N;
-        if (boss) load_env(n2, pend);
+        if (boss) {
+            if (n2 >= N) { n2 = N; more = false; }
+            load_env(n2, pend);
+        }
         if (worker) {   // zero frame (everything outside the window stays zero)
             const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
             for (int i = tid; i < (tile_bytes >> 4); i += kFlexThreads) reinterpret_cast<uint4 *>(s_tile)[i] = z4;
@@ -2040,11 +2046,11 @@ __global__ void __launch_bounds__(kFlexThreads + 32, 2) k_observe_flexible_v3(co
             if (k0) __syncthreads();           // the previous group's H pass has read t1
             if (!worker) {
             } else if (blur) {
-                if (nh == 1) flex_wpass<1>(s_x + k0 * rh * nwxp, nwxp, s_xw, s_wq, s_t1, g.rwp, sb, cb, rw, kc * rh, tid);
-                else flex_wpass<2>(s_x + k0 * rh * nwxp, nwxp, s_xw, s_wq, s_t1, g.rwp, sb, cb, rw, kc * rh, tid);
+                if (nh == 1) flex_wpass<1>(s_x + k0 * rh * nwxp, nwxp, s_xw, s_wq, s_t1, g.rwp, sb, cb, rw, kc * rh, tid, s_magic);
+                else flex_wpass<2>(s_x + k0 * rh * nwxp, nwxp, s_xw, s_wq, s_t1, g.rwp, sb, cb, rw, kc * rh, tid, s_magic);
             } else {
                 // the window itself, bit exact: output words (bytes outside the window masked to zero) parked in t1
-                const FastDiv fd_nq(g.nq);
+                const FastDiv fd_nq(g.nq, s_magic);
                 const uint32_t sh = (uint32_t)(cb - sb) * 8u;
                 uint32_t *t1w = reinterpret_cast<uint32_t *>(s_t1);
                 for (int i = tid; i < kc * rh * g.nq; i += kFlexThreads) {
@@ -2063,14 +2069,14 @@ __global__ void __launch_bounds__(kFlexThreads + 32, 2) k_observe_flexible_v3(co
             if (last) prefetch((j + 1) & (kWin - 1));
             if (blur) {
                 switch (th) {
-                    case 3: flex_hpass<3>(g, s_t1, s_wh2, s_xh, s_tile, k0, kc, th, tid); break;
-                    case 4: flex_hpass<4>(g, s_t1, s_wh2, s_xh, s_tile, k0, kc, th, tid); break;
-                    case 5: flex_hpass<5>(g, s_t1, s_wh2, s_xh, s_tile, k0, kc, th, tid); break;
-                    case 6: flex_hpass<6>(g, s_t1, s_wh2, s_xh, s_tile, k0, kc, th, tid); break;
-                    default: flex_hpass<0>(g, s_t1, s_wh2, s_xh, s_tile, k0, kc, th, tid); break;
+                    case 3: flex_hpass<3>(g, s_t1, s_wh2, s_xh, s_tile, k0, kc, th, tid, s_magic); break;
+                    case 4: flex_hpass<4>(g, s_t1, s_wh2, s_xh, s_tile, k0, kc, th, tid, s_magic); break;
+                    case 5: flex_hpass<5>(g, s_t1, s_wh2, s_xh, s_tile, k0, kc, th, tid, s_magic); break;
+                    case 6: flex_hpass<6>(g, s_t1, s_wh2, s_xh, s_tile, k0, kc, th, tid, s_magic); break;
+                    default: flex_hpass<0>(g, s_t1, s_wh2, s_xh, s_tile, k0, kc, th, tid, s_magic); break;
                 }
             } else {
-                const FastDiv fd_nq(g.nq), fd_rh(rh);
+                const FastDiv fd_nq(g.nq, s_magic), fd_rh(rh, s_magic);
                 const uint32_t *t1w = reinterpret_cast<const uint32_t *>(s_t1);
                 for (int i = tid; i < kc * rh * g.nq; i += kFlexThreads) {
                     const int row = fd_nq.div(i), q = i - row * g.nq;
@@ -2344,7 +2350,7 @@ cudaError_t launch_observe_flexible(const DevPlan &p, const uint8_t *ring, const
         const size_t tile = (size_t)p.K * oh * ow;
         const size_t fixed = a16(tile + 4 * (size_t)p.K * p.S_h * (p.S_w / 4 + 2)) +
                              4 * ((size_t)p.S_w * 8 + 2 * (size_t)p.S_h * p.blur_tmax + p.S_w + p.S_h) + 16;
-        const size_t budget = 115000;  // + static shared memory + 1 KB reserved per CTA: two CTAs per SM (233,472 B)
+        const size_t budget = 114000;  // + static shared memory + 1 KB reserved per CTA: two CTAs per SM (233,472 B)
         const size_t one = (size_t)p.S_h * (p.S_w + 4), all = (size_t)p.K * one;   // floats: one / all K frames of the largest window
         const size_t room = budget > fixed ? ((budget - fixed) / 4) & ~size_t(3) : 0;
         const size_t t1_cap = std::min(all, room);
