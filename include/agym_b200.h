@@ -11,7 +11,9 @@
  *   - plain C, no torch / C++ types; every function returns 0 (AGYM_OK) or a negative
  *     agym_status, or a positive cudaError_t from the launch; nothing throws or exits.
  *   - the caller owns every buffer passed in.  `d_` parameters are DEVICE pointers on the current device,
- *     `h_` parameters are HOST pointers.  A plan owns only its small coefficient tables.
+ *     `h_` parameters are HOST pointers.  A plan owns only its small coefficient tables and a 16-byte work
+ *     counter used by agym_observe_flexible (zero between launches); calls on one plan are stream-ordered:
+ *     do not run the same plan's agym_observe_flexible on two streams at once (one plan per stream/shard).
  *   - all device work is enqueued on `stream` (a cudaStream_t passed as void*); no
  *     function synchronises unless its name ends in `_host`.
  *   - buffers should be 16-byte aligned (any cudaMalloc / torch allocation is): the TMA bulk-copy paths
@@ -147,7 +149,10 @@ AGYM_API int agym_observe_peripheral(const agym_plan *plan, const uint8_t *d_rin
 
 /* Replaces FlexibleFovealEnv._fov_step + _get_fov_state (fov_env.py:270-330).
  * d_atype: i32 [N] (NULL = all FOV_LOC).  CROP writes the variable-size patch into the
- * top-left corner of a zeroed [N][K][pad_h][pad_w] buffer (pad >= the largest res). */
+ * top-left corner of a zeroed [N][K][pad_h][pad_w] buffer (pad >= the largest res).
+ * Blurred pixels (res rows > fov rows) are within 0.5 LSB + 0.02 of the reference's float value: the W-axis
+ * operator runs in 16-bit fixed point (<= 255 * taps / 2^17 LSB from the fp64 weights); windows that the
+ * reference does not blur, the mask and the padding are bit exact. */
 AGYM_API int agym_observe_flexible(const agym_plan *plan, const uint8_t *d_ring, const int32_t *d_head,
                           const double *d_action, const int32_t *d_atype, const uint8_t *d_fov_ctrl,
                           int32_t *d_loc, int32_t *d_res, int variant, int pad_h, int pad_w,
