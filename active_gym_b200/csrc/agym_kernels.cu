@@ -1768,6 +1768,81 @@ __global__ void __launch_bounds__(kThreads) k_observe_flexible_fast(const __grid
     }
 }
 
+// Crop variant, second version: still one warp per env, but the K windows are first staged in the warp's
+// own shared-memory slice as ALIGNED words (25 independent 4-byte loads per lane instead of 85 byte loads in
+// five dependent rounds: one DRAM round trip per env), and the output words are then gathered from shared
+// memory through a CTA-wide table of byte offsets that is the same for every env (it only depends on K, f).
+// Requires f_h * f_w % 4 == 0 is NOT needed: the table is flat over the K * f_h * f_w output bytes.
+constexpr int kCropWarps = 8;
+__global__ void __launch_bounds__(kCropWarps * 32) k_observe_fixed_crop_v2(const __grid_constant__ DevPlan p,
+                                                                           const uint8_t *__restrict__ ring,
+                                                                           const int32_t *__restrict__ head,
+                                                                           const double *__restrict__ action,
+                                                                           const uint8_t *__restrict__ ctrl,
+                                                                           int32_t *__restrict__ loc, uint8_t *__restrict__ out,
+                                                                           int nwx) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int K = p.K, per_k = p.f_h * p.f_w, words = (K * per_k) >> 2, rows = K * p.f_h, quads = p.S_w >> 2;
+    const int stride = nwx * 4;                                   // staged bytes per window row
+    uint2 *s_off = reinterpret_cast<uint2 *>(smem);               // [words] 4 x u16: staged byte offset of each output byte
+    uint32_t *s_win = reinterpret_cast<uint32_t *>(smem + align16((size_t)words * 8)) + warp * rows * nwx;
+    const int n = blockIdx.x * kCropWarps + warp;
+    const bool valid = n < p.N;
+    // the loads of the fov update go out first: their latency hides behind the table build
+    LocIn li;
+    li.a0 = li.a1 = 0.0; li.r = li.c = 0; li.mode = AGYM_FOV_KEEP;
+    if (valid && lane == 0) li = load_loc_in(n, action, ctrl, loc);
+    const int h = valid ? head[n] : 0;
+    {
+        const FastDiv fd_w(p.f_w);
+        for (int t = tid; t < words; t += kCropWarps * 32) {
+            uint32_t o[4];
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const int idx = 4 * t + b, row = fd_w.div(idx), x = idx - row * p.f_w;  // row = k * f_h + y
+                o[b] = (uint32_t)(row * stride + x);
+            }
+            s_off[t] = make_uint2(o[0] | (o[1] << 16), o[2] | (o[3] << 16));
+        }
+    }
+    int r0 = 0, c0 = 0;
+    if (valid && lane == 0) {
+        apply_loc(p, li, r0, c0);
+        loc[2 * n] = r0;
+        loc[2 * n + 1] = c0;
+    }
+    r0 = __shfl_sync(0xffffffffu, r0, 0);
+    c0 = __shfl_sync(0xffffffffu, c0, 0);
+    const int wq0 = c0 >> 2, cb = c0 & 3;
+    if (valid) {
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(ring) + (size_t)n * K * (p.plane >> 2) + r0 * quads + wq0;
+        const FastDiv fd_n(nwx), fd_h(p.f_h);
+        const int wmax = quads - 1 - wq0;   // last word of a frame row: the spare staged word must not run past the ring
+#pragma unroll 4
+        for (int i = lane; i < rows * nwx; i += 32) {
+            const int row = fd_n.div(i), w = i - row * nwx;
+            const int k = fd_h.div(row), y = row - k * p.f_h;
+            int slot = h + 1 + k;
+            slot -= slot >= K ? K : 0;
+            cp_async4(s_win + i, src + slot * (p.plane >> 2) + y * quads + min(w, wmax));
+        }
+    }
+    cp_async_commit();
+    __syncthreads();   // offset table complete
+    if (!valid) return;
+    cp_async_wait<0>();
+    __syncwarp();
+    const uint8_t *wb = reinterpret_cast<const uint8_t *>(s_win) + cb;
+    uint32_t *dst = reinterpret_cast<uint32_t *>(out + (size_t)n * K * per_k);
+#pragma unroll 4
+    for (int t = lane; t < words; t += 32) {
+        const uint2 o = s_off[t];
+        const uint32_t b0 = wb[o.x & 0xffffu], b1 = wb[o.x >> 16], b2 = wb[o.y & 0xffffu], b3 = wb[o.y >> 16];
+        dst[t] = __byte_perm(__byte_perm(b0, b1, 0x0040), __byte_perm(b2, b3, 0x0040), 0x5410);
+    }
+}
+
 // Persistent flexible fovea (mask_out in place, or the zero-padded crop): the successor of
 // k_observe_flexible_fast.  Two CTAs per SM pull envs from a device counter (windows of 20..50 pixels,
 // blurred or not, make an env's cost vary 3x: a static split left a quarter of the SM time idle) and
@@ -2174,6 +2249,8 @@ const bool g_disable_std = getenv("AGYM_NO_STD") != nullptr;
 const bool g_disable_tma = getenv("AGYM_NO_TMA") != nullptr;
 // AGYM_FLEX_OLD=1 forces the one-CTA-per-env flexible kernel (A/B comparisons)
 const bool g_flex_old = getenv("AGYM_FLEX_OLD") != nullptr;
+// AGYM_CROP_OLD=1 forces the byte-gather crop kernel (A/B comparisons)
+const bool g_crop_old = getenv("AGYM_CROP_OLD") != nullptr;
 // AGYM_INGEST_UNITS=n: units (shared-memory stages) per env of the TMA ingest kernel (tuning)
 const int g_units = getenv("AGYM_INGEST_UNITS") ? atoi(getenv("AGYM_INGEST_UNITS")) : 0;
 
@@ -2248,7 +2325,13 @@ cudaError_t launch_stack(const DevPlan &p, const uint8_t *ring, const int32_t *h
 cudaError_t launch_observe_fixed(const DevPlan &p, const uint8_t *ring, const int32_t *head, const double *action,
                                  const uint8_t *ctrl, int32_t *loc, int variant, uint8_t *out, cudaStream_t st) {
     cudaError_t e;
-    if (variant == AGYM_OUT_CROP && (p.K * p.f_h * p.f_w) % 4 == 0 && !g_disable_std) {
+    const int crop_nwx = (p.f_w + 2) / 4 + 1;  // aligned words that cover f_w bytes at any byte offset
+    const size_t crop_smem = a16((size_t)(p.K * p.f_h * p.f_w / 4) * 8) + (size_t)kCropWarps * p.K * p.f_h * crop_nwx * 4;
+    if (variant == AGYM_OUT_CROP && (p.K * p.f_h * p.f_w) % 4 == 0 && !g_disable_std && !g_crop_old &&
+        crop_smem <= 64 * 1024 && p.K * p.f_h * crop_nwx * 4 + 4 < 65536) {
+        if ((e = set_smem(k_observe_fixed_crop_v2, crop_smem)) != cudaSuccess) return e;
+        k_observe_fixed_crop_v2<<<(p.N + kCropWarps - 1) / kCropWarps, kCropWarps * 32, crop_smem, st>>>(p, ring, head, action, ctrl, loc, out, crop_nwx);
+    } else if (variant == AGYM_OUT_CROP && (p.K * p.f_h * p.f_w) % 4 == 0 && !g_disable_std) {
         k_observe_fixed_crop_warp<<<(p.N + kThreads / 32 - 1) / (kThreads / 32), kThreads, 0, st>>>(p, ring, head, action, ctrl, loc, out);
     } else if (variant == AGYM_OUT_CROP) {
         k_observe_fixed<AGYM_OUT_CROP><<<p.N, kThreads, 0, st>>>(p, ring, head, action, ctrl, loc, out);
