@@ -236,6 +236,7 @@ int agym_plan_create(const agym_config *cfg, agym_plan **out_plan) {
     // ingest: dp2a form of the horizontal pass, two output columns per thread
     bool fast_ingest = (c.obs_w % 2 == 0) && (c.obs_w / 2 <= 256);
     std::vector<int32_t> pair_tab, ybs_tab;
+    bool fast_ingest_rgb = true;
     for (int x0 = 0; fast_ingest && x0 < c.obs_w; x0 += 2) {
         const int s[4] = {cx.s0[x0], cx.s1[x0], cx.s0[x0 + 1], cx.s1[x0 + 1]};
         const int base = s[0] & ~3;
@@ -246,6 +247,7 @@ int agym_plan_create(const agym_config *cfg, agym_plan **out_plan) {
             sel |= (o & 7) << (4 * k);
         }
         pair_tab.insert(pair_tab.end(), {base, sel, cx.coef[x0], cx.coef[x0 + 1]});
+        for (int k = 0; k < 4; ++k) fast_ingest_rgb = fast_ingest_rgb && s[k] - s[0] >= 0 && s[k] - s[0] <= 3;
     }
     for (int y = 0; y < c.obs_h; ++y) {
         ybs_tab.push_back((cy.coef[y] & 0xffff) << 16);
@@ -376,8 +378,9 @@ int agym_plan_create(const agym_config *cfg, agym_plan **out_plan) {
     d.pool_i = reinterpret_cast<const int32_t *>(base);
     d.S_max = s_max;
     d.fast_ingest = fast_ingest;
+    d.fast_ingest_rgb = fast_ingest && fast_ingest_rgb && c.raw_c == 3;
     auto spans = [&](const std::vector<int32_t> &s0, const std::vector<int32_t> &s1, int32_t *out4) {
-        for (int u = 1; u <= 4; ++u) {  // row span of the largest unit when the output rows are cut into u units
+        for (int u = 1; u <= 8; ++u) {  // row span of the largest unit when the output rows are cut into u units
             out4[u - 1] = 0;
             if (c.obs_h % u != 0) continue;
             const int R = c.obs_h / u;
@@ -389,7 +392,7 @@ int agym_plan_create(const agym_config *cfg, agym_plan **out_plan) {
                 span = std::max(span, hi - lo + 1);
             }
             // a stage holds both frames' spans; keep two stages well inside one SM's shared memory
-            if (monotone && 2 * (2 * (static_cast<size_t>(span) * c.raw_w + 16)) <= 96 * 1024) out4[u - 1] = span;
+            if (monotone && 2 * (2 * (static_cast<size_t>(span) * c.raw_w * c.raw_c + 16)) <= 96 * 1024) out4[u - 1] = span;
         }
     };
     spans(cy.s0, cy.s1, d.tma_span_rows);

@@ -512,7 +512,7 @@ __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;"
 constexpr int kIngestThreads = kThreads + 32;
 constexpr int kStages = 2;
 
-template <int RAW_W, int S_W>
+template <int RAW_W, int S_W, int CH>  // RAW_W: BYTES per raw row (pixels * CH) when baked in
 __global__ void __launch_bounds__(kIngestThreads, 3) k_ingest_atari_tma(const __grid_constant__ DevPlan p,
                                                                         const uint8_t *__restrict__ fa,
                                                                         const uint8_t *__restrict__ fb,
@@ -527,7 +527,7 @@ __global__ void __launch_bounds__(kIngestThreads, 3) k_ingest_atari_tma(const __
     __shared__ int s_envfl[kEnvWin], s_envhd[kEnvWin];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int N = p.N, K = p.K;
-    const int raw_w = RAW_W ? RAW_W : p.raw_w;
+    const int raw_w = RAW_W ? RAW_W : p.raw_w * CH;               // bytes per raw row
     const int S_w = S_W ? S_W : p.S_w;
     const int R = p.S_h / units;                          // output rows per unit
     const int frame_stride = span_rows * raw_w + 16;      // one frame's staged row span of a unit (+ pad)
@@ -597,6 +597,35 @@ __global__ void __launch_bounds__(kIngestThreads, 3) k_ingest_atari_tma(const __
     const int g = tid / pairs, pi = tid - g * pairs;
     const bool worker = g < segs;
     const int4 px = worker ? __ldg(p.cx_pair + pi) : make_int4(0, 0, 0, 0);
+    // RGB: the four source pixels of this column pair lie among s0 .. s0 + 3 (checked when the plan was made):
+    // 12 bytes starting at byte 3 * s0 of the row
+    const int s0px = px.x + (px.y & 7);
+    const int tap_off = CH == 1 ? px.x : ((3 * s0px) & ~3);
+    const uint32_t rgb_sh = (uint32_t)((3 * s0px) & 3) * 8u;
+    uint32_t rgb_sel = 0u;
+    if (CH == 3) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int rel = ((px.y >> (4 * k)) & 7) - (px.y & 7);  // 0..3: which of the four lumas
+            rgb_sel |= (uint32_t)(rel < 2 ? rel : rel + 2) << (4 * k);
+        }
+    }
+    const uint32_t lw_a = (2u * p.lw0) | ((2u * p.lw1) << 16), lw_b = 2u * p.lw2;
+    const uint32_t lw_c = (2u * p.lw0) << 16, lw_d = (2u * p.lw1) | ((2u * p.lw2) << 16);
+    // the 4 source bytes {s0(x0), s1(x0), s0(x0+1), s1(x0+1)} of one raw row, as the IDP.2A operand
+    auto tap4 = [&](const uint8_t *row) -> uint32_t {
+        const uint32_t *w = reinterpret_cast<const uint32_t *>(row);
+        if (CH == 1) return __byte_perm(w[0], w[1], (uint32_t)px.y);
+        // cv2 luma Y = (lw . c + 16384) >> 15 = byte 2 of 2 (lw . c) + 32768, for 4 consecutive RGB pixels:
+        // v0 = R0 G0 B0 R1, v1 = G1 B1 R2 G2, v2 = B2 R3 G3 B3
+        const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3];
+        const uint32_t v0 = __funnelshift_r(w0, w1, rgb_sh), v1 = __funnelshift_r(w1, w2, rgb_sh), v2 = __funnelshift_r(w2, w3, rgb_sh);
+        const uint32_t y0 = __dp2a_hi(lw_b, v0, __dp2a_lo(lw_a, v0, 32768u));
+        const uint32_t y1 = __dp2a_lo(lw_d, v1, __dp2a_hi(lw_c, v0, 32768u));
+        const uint32_t y2 = __dp2a_lo(lw_b, v2, __dp2a_hi(lw_a, v1, 32768u));
+        const uint32_t y3 = __dp2a_hi(lw_d, v2, __dp2a_lo(lw_c, v2, 32768u));
+        return __byte_perm(__byte_perm(y0, y1, 0x0062), __byte_perm(y2, y3, 0x0062), rgb_sel);
+    };
     const int rows_per = (R + segs - 1) / segs;
     const int yy_begin = g * rows_per, yy_end = worker ? min(R, yy_begin + rows_per) : yy_begin;
     // squeeze along W: one thread = one output column i, rows in passes
@@ -629,7 +658,7 @@ __global__ void __launch_bounds__(kIngestThreads, 3) k_ingest_atari_tma(const __
         const bool idle = fl & AGYM_FLAG_IDLE;
         mbar_wait(&full[st], ph);
         if (!idle && yy_begin < yy_end) {
-            const uint8_t *base = stages + st * stage_bytes + px.x;
+            const uint8_t *base = stages + st * stage_bytes + tap_off;
             const int4 *rw = s_row + part * R + yy_begin;
             uint8_t *o = s_frame + (part * R + yy_begin) * S_w + 2 * pi;
             if ((fl & 3) == 3) {  // both frames (the steady state)
@@ -642,11 +671,7 @@ __global__ void __launch_bounds__(kIngestThreads, 3) k_ingest_atari_tma(const __
                     uint32_t m0 = 0u, m1 = 0u;
 #pragma unroll
                     for (int fr = 0; fr < 2; ++fr) {
-                        const uint32_t a0 = *reinterpret_cast<const uint32_t *>(ra + fr * frame_stride);
-                        const uint32_t a1 = *reinterpret_cast<const uint32_t *>(ra + fr * frame_stride + 4);
-                        const uint32_t b0 = *reinterpret_cast<const uint32_t *>(rb + fr * frame_stride);
-                        const uint32_t b1 = *reinterpret_cast<const uint32_t *>(rb + fr * frame_stride + 4);
-                        const uint32_t qa = __byte_perm(a0, a1, (uint32_t)px.y), qb = __byte_perm(b0, b1, (uint32_t)px.y);
+                        const uint32_t qa = tap4(ra + fr * frame_stride), qb = tap4(rb + fr * frame_stride);
                         const uint32_t h00 = __dp2a_lo((uint32_t)px.z, qa, 0u), h01 = __dp2a_hi((uint32_t)px.w, qa, 0u);
                         const uint32_t h10 = __dp2a_lo((uint32_t)px.z, qb, 0u), h11 = __dp2a_hi((uint32_t)px.w, qb, 0u);
                         m0 = max(m0, __umulhi((uint32_t)t.z, h00 >> 4) + __umulhi((uint32_t)t.w, h10 >> 4));
@@ -661,11 +686,7 @@ __global__ void __launch_bounds__(kIngestThreads, 3) k_ingest_atari_tma(const __
                     for (int fr = 0; fr < 2; ++fr) {
                         if (!(fl & (1 << fr))) continue;
                         const uint8_t *ra = base + t.x + fr * frame_stride, *rb = base + t.y + fr * frame_stride;
-                        const uint32_t a0 = *reinterpret_cast<const uint32_t *>(ra);
-                        const uint32_t a1 = *reinterpret_cast<const uint32_t *>(ra + 4);
-                        const uint32_t b0 = *reinterpret_cast<const uint32_t *>(rb);
-                        const uint32_t b1 = *reinterpret_cast<const uint32_t *>(rb + 4);
-                        const uint32_t qa = __byte_perm(a0, a1, (uint32_t)px.y), qb = __byte_perm(b0, b1, (uint32_t)px.y);
+                        const uint32_t qa = tap4(ra), qb = tap4(rb);
                         const uint32_t h00 = __dp2a_lo((uint32_t)px.z, qa, 0u), h01 = __dp2a_hi((uint32_t)px.w, qa, 0u);
                         const uint32_t h10 = __dp2a_lo((uint32_t)px.z, qb, 0u), h11 = __dp2a_hi((uint32_t)px.w, qb, 0u);
                         m0 = max(m0, (__umulhi((uint32_t)t.z, h00 >> 4) + __umulhi((uint32_t)t.w, h10 >> 4) + 2u) >> 2);
@@ -2262,13 +2283,16 @@ cudaError_t launch_ingest_atari(const DevPlan &p, const uint8_t *fa, const uint8
     size_t smem = a16(sizeof(int32_t) * 3 * (p.S_w + p.S_h)) + a16(2 * (size_t)2 * p.S_h * p.raw_w);
     if (pcache) smem += a16(p.plane) + sizeof(float) * p.S_h * p.p_w;
     cudaError_t e;
-    int ui = std::min(std::max(g_units ? g_units : 3, 1), 4);  // units per env: index into the plan's span table
+    // units per env: index into the plan's span table (gray: 3 units of 28 rows; RGB: 7 units of 12 rows = two rows
+    // for each of the 6 row segments of the consumer warps, and three CTAs still fit an SM)
+    int ui = std::min(std::max(g_units ? g_units : (p.raw_c == 3 ? 7 : 3), 1), 8);
     while (ui > 1 && p.tma_span_rows[ui - 1] == 0) --ui;
     if (p.tma_span_rows[ui - 1] == 0)
-        for (ui = 4; ui > 1 && p.tma_span_rows[ui - 1] == 0;) --ui;
-    if (p.fast_ingest && p.raw_c == 1 && !g_disable_tma && p.tma_span_rows[ui - 1] > 0) {
+        for (ui = 8; ui > 1 && p.tma_span_rows[ui - 1] == 0;) --ui;
+    const bool tma_ok = p.raw_c == 1 || (p.raw_c == 3 && p.fast_ingest_rgb);
+    if (p.fast_ingest && tma_ok && !g_disable_tma && p.tma_span_rows[ui - 1] > 0) {
         const int units = ui, span_rows = p.tma_span_rows[ui - 1];
-        const size_t stage = a16(2 * ((size_t)span_rows * p.raw_w + 16));
+        const size_t stage = a16(2 * ((size_t)span_rows * p.raw_w * p.raw_c + 16));
         size_t fs = 2 * stage + a16(p.plane + 16) + 16 * (size_t)p.S_h + 8 * (size_t)((units + 1) & ~1);
         if (pcache) fs += sizeof(float) * ((size_t)p.S_h * p.p_w + (size_t)p.p_w * 24 + (size_t)p.p_h * p.sq_h.taps + (size_t)p.p_h);
         int dev = 0, sms = 148, occ = 1;
@@ -2281,8 +2305,11 @@ cudaError_t launch_ingest_atari(const DevPlan &p, const uint8_t *fa, const uint8
         k_ingest_atari_tma<__VA_ARGS__><<<std::min(p.N, sms * std::max(occ, 1)), kIngestThreads, fs, st>>>(         \
             p, fa, fb, flags, ring, head, pcache, units, span_rows);                                                \
     }
-        if (p.raw_w == 160 && p.S_w == 84) AGYM_LAUNCH_TMA(160, 84)
-        else AGYM_LAUNCH_TMA(0, 0)
+        if (p.raw_c == 3) {
+            if (p.raw_w == 160 && p.S_w == 84) AGYM_LAUNCH_TMA(480, 84, 3)
+            else AGYM_LAUNCH_TMA(0, 0, 3)
+        } else if (p.raw_w == 160 && p.S_w == 84) AGYM_LAUNCH_TMA(160, 84, 1)
+        else AGYM_LAUNCH_TMA(0, 0, 1)
 #undef AGYM_LAUNCH_TMA
         return cudaGetLastError();
     }

@@ -51,7 +51,8 @@ struct DevPlan {
     // ingest: per output-column pair {byte offset of the aligned word, PRMT selector, coef(x0), coef(x0+1)}
     // and per output row {b0 << 16, b1 << 16} (atari_env.py:74 fixed-point bilinear, dp2a form)
     int32_t fast_ingest;
-    int32_t tma_span_rows[4];  // TMA ingest: largest source-row span of a unit when an env is cut into 1..4 units (0 = n/a)
+    int32_t tma_span_rows[8];  // TMA ingest: largest source-row span of a unit when an env is cut into 1..8 units (0 = n/a)
+    int32_t fast_ingest_rgb;   // 3-channel frames: every column pair's four source pixels lie among s0 .. s0 + 3
     const int4 *cx_pair;    // [S_w / 2]
     const int2 *cy_bs;      // [S_h]
     // squeeze along W from u8 rows: per output column {aligned byte offset, shift, first weight index}

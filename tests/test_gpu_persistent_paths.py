@@ -55,6 +55,23 @@ def test_tma_ingest_many_envs_per_cta_ragged(n):
     assert (cached.int() - direct.int()).abs().max().item() <= 1
 
 
+@pytest.mark.parametrize("n", [449, 1400])
+def test_tma_ingest_rgb_many_envs_per_cta_ragged(n):
+    """3-channel frames through the persistent TMA ingest (luma fused into the horizontal pass): bit exact."""
+    rng = np.random.default_rng(3 * n)
+    K = 4
+    p = _path(n, K, raw=(210, 160, 3), fov_size=(30, 30))
+    ring, head = orc.new_state(n, K, S)
+    for step in range(3):
+        fa = rng.integers(0, 256, (n, 210, 160, 3), dtype=np.uint8)
+        fb = rng.integers(0, 256, (n, 210, 160, 3), dtype=np.uint8)
+        fl = np.full(n, 5, np.uint8) if step == 0 else _flags(rng, n)
+        p.ingest_atari(fa, fb, fl)
+        orc.ingest_atari(fa, fb, fl, ring, head)
+        assert np.array_equal(_np(p.head), head), step
+        assert np.array_equal(_np(p.ring), ring), step
+
+
 @pytest.mark.parametrize("K,n", [(4, 700), (3, 611), (4, 297)])
 def test_peripheral_std_kernel_all_envs_vs_oracle(K, n):
     rng = np.random.default_rng(100 + n)
