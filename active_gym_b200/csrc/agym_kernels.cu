@@ -823,24 +823,52 @@ __global__ void __launch_bounds__(kThreads) k_ingest_dmc(const __grid_constant__
                                                          float *__restrict__ pcache) {
     extern __shared__ __align__(16) uint8_t smem[];
     const int n = blockIdx.x, tid = threadIdx.x;
+    const uint8_t *src = f + (size_t)n * p.plane * 3;
+    const int nvec = p.plane / 16;
+    // the frame words of this thread's first two 16-pixel groups are requested before flags / head are known
+    // (an idle env wastes them): one DRAM round trip per CTA instead of two
+    uint32_t w0[12], w1[12];
+    const int t0 = tid, t1 = tid + kThreads;
+    if (t0 < nvec) {
+        const uint8_t *q = src + (size_t)t0 * 48;
+        *reinterpret_cast<uint4 *>(w0) = ld_stream128(q);
+        *reinterpret_cast<uint4 *>(w0 + 4) = ld_stream128(q + 16);
+        *reinterpret_cast<uint4 *>(w0 + 8) = ld_stream128(q + 32);
+    }
+    if (t1 < nvec) {
+        const uint8_t *q = src + (size_t)t1 * 48;
+        *reinterpret_cast<uint4 *>(w1) = ld_stream128(q);
+        *reinterpret_cast<uint4 *>(w1 + 4) = ld_stream128(q + 16);
+        *reinterpret_cast<uint4 *>(w1 + 8) = ld_stream128(q + 32);
+    }
     const int fl = flags[n];
+    const int hd = head[n];
     if (fl & AGYM_FLAG_IDLE) return;
-    const int slot = (head[n] + 1) % p.K;
+    const int slot = (hd + 1) % p.K;
     uint8_t *s_frame = smem;
     float *s_t1 = reinterpret_cast<float *>(smem + align16(p.plane));
     __syncthreads();
     if (tid == 0) head[n] = slot;
 
-    const uint8_t *src = f + (size_t)n * p.plane * 3;
     uint4 *dst = reinterpret_cast<uint4 *>(ring + ((size_t)n * p.K + slot) * p.plane);
-#pragma unroll 2
-    for (int t = tid; t < p.plane / 16; t += kThreads) {
+    const uint32_t lw01 = (2u * p.lw0) | ((2u * p.lw1) << 16), lw2 = 2u * p.lw2;
+    if (t0 < nvec) {
+        const uint4 o = luma16(w0, lw01, lw2);
+        dst[t0] = o;
+        if (pcache) reinterpret_cast<uint4 *>(s_frame)[t0] = o;
+    }
+    if (t1 < nvec) {
+        const uint4 o = luma16(w1, lw01, lw2);
+        dst[t1] = o;
+        if (pcache) reinterpret_cast<uint4 *>(s_frame)[t1] = o;
+    }
+    for (int t = tid + 2 * kThreads; t < nvec; t += kThreads) {  // larger observations
         uint32_t w[12];
         const uint8_t *q = src + (size_t)t * 48;
         *reinterpret_cast<uint4 *>(w) = ld_stream128(q);
         *reinterpret_cast<uint4 *>(w + 4) = ld_stream128(q + 16);
         *reinterpret_cast<uint4 *>(w + 8) = ld_stream128(q + 32);
-        const uint4 o = luma16(w, (2u * p.lw0) | ((2u * p.lw1) << 16), 2u * p.lw2);
+        const uint4 o = luma16(w, lw01, lw2);
         dst[t] = o;
         if (pcache) reinterpret_cast<uint4 *>(s_frame)[t] = o;
     }
