@@ -26,7 +26,7 @@ EXPORTS = (
     "agym_abi_version", "agym_status_string", "agym_plan_create", "agym_plan_destroy",
     "agym_plan_ring_bytes", "agym_plan_pcache_bytes", "agym_ingest_atari", "agym_ingest_dmc",
     "agym_stack", "agym_observe_fixed", "agym_observe_peripheral", "agym_observe_flexible",
-    "agym_synth_frames", "agym_table_cv2", "agym_table_aa", "agym_normalize", "agym_plan_used_rows", "agym_ingest_atari_packed",
+    "agym_synth_frames", "agym_table_cv2", "agym_table_aa", "agym_table_blur", "agym_normalize", "agym_plan_used_rows", "agym_ingest_atari_packed",
 )
 
 
@@ -74,6 +74,7 @@ def lib() -> C.CDLL:
     L.agym_normalize.argtypes = [vp, sz, i32, vp, vp]
     L.agym_table_cv2.argtypes = [i32, i32, i32, vp, vp, vp]
     L.agym_table_aa.argtypes = [i32, i32, vp, vp, sz, vp]
+    L.agym_table_blur.argtypes = [i32, i32, vp, vp, vp, sz, vp, vp]
     if L.agym_abi_version() != ABI_VERSION:
         raise RuntimeError(f"libagym_b200 ABI {L.agym_abi_version()} != expected {ABI_VERSION}; rebuild")
     _lib = L

@@ -189,27 +189,9 @@ int agym_plan_create(const agym_config *cfg, agym_plan **out_plan) {
             std::vector<int32_t> qindex(static_cast<size_t>(s_max + 1) * 4, 0);
             for (int r = 1; r <= c.obs_w; ++r) {
                 const AaAxis ax = build_blur_axis(r, c.fov_w);
-                const int nh = (ax.taps + 7) / 8;
-                std::vector<int32_t> q(static_cast<size_t>(r) * nh * 4, 0);
-                for (int x = 0; x < r; ++x) {
-                    int64_t v[16] = {0}, sum = 0;
-                    double frac[16] = {0};
-                    for (int t = 0; t < ax.taps; ++t) {
-                        const double w = static_cast<double>(ax.w[static_cast<size_t>(x) * ax.taps + t]) * 65536.0;
-                        v[t] = static_cast<int64_t>(std::floor(w));
-                        frac[t] = w - std::floor(w);
-                        sum += v[t];
-                    }
-                    for (int64_t left = 65536 - sum; left > 0; --left) {  // hand the missing units to the largest remainders
-                        int best = 0;
-                        for (int t = 1; t < ax.taps; ++t) if (frac[t] > frac[best]) best = t;
-                        if (frac[best] <= 0.0) break;
-                        ++v[best]; frac[best] = -1.0;
-                    }
-                    for (int t = 0; t < 16; ++t) v[t] = std::min<int64_t>(std::max<int64_t>(v[t], 0), 65535);
-                    for (int t = 0; t < nh * 8; t += 2)
-                        q[static_cast<size_t>(x) * nh * 4 + t / 2] = static_cast<int32_t>(static_cast<uint32_t>(v[t]) | (static_cast<uint32_t>(v[t + 1]) << 16));
-                }
+                int nh = 1;
+                const std::vector<uint32_t> qu = quantize_axis_q16(ax, &nh);
+                const std::vector<int32_t> q(qu.begin(), qu.end());
                 int32_t *e = qindex.data() + static_cast<size_t>(r) * 4;
                 e[0] = static_cast<int32_t>(pool.add_i(ax.xmin)); e[1] = static_cast<int32_t>(pool.add_i(q));
                 e[2] = nh; e[3] = ax.taps;
@@ -532,6 +514,20 @@ int agym_table_aa(int n_in, int n_out, int32_t *h_xmin, float *h_w, size_t w_cap
     std::memcpy(h_xmin, ax.xmin.data(), sizeof(int32_t) * n_out);
     std::memcpy(h_w, ax.w.data(), sizeof(float) * ax.w.size());
     *taps = ax.taps;
+    return AGYM_OK;
+}
+
+int agym_table_blur(int r, int f, int32_t *h_xmin, float *h_w, uint16_t *h_q, size_t capacity, int32_t *taps, int32_t *halves) {
+    if (r <= 0 || f <= 0 || !h_xmin || !h_w || !h_q || !taps || !halves) return AGYM_ERR_INVALID_ARG;
+    const AaAxis ax = build_blur_axis(r, f);
+    int nh = 1;
+    const std::vector<uint32_t> q = quantize_axis_q16(ax, &nh);
+    if (ax.w.size() > capacity || q.size() * 2 > capacity) return AGYM_ERR_INVALID_ARG;
+    std::memcpy(h_xmin, ax.xmin.data(), sizeof(int32_t) * r);
+    std::memcpy(h_w, ax.w.data(), sizeof(float) * ax.w.size());
+    std::memcpy(h_q, q.data(), sizeof(uint32_t) * q.size());
+    *taps = ax.taps;
+    *halves = nh;
     return AGYM_OK;
 }
 

@@ -121,4 +121,35 @@ AaAxis build_blur_axis(int r, int f) {
     return ax;
 }
 
+std::vector<uint32_t> quantize_axis_q16(const AaAxis &ax, int *halves) {
+    const int nh = (ax.taps + 7) / 8;
+    if (halves) *halves = nh;
+    std::vector<uint32_t> q(static_cast<size_t>(ax.n_out) * nh * 4, 0u);
+    std::vector<int64_t> v(static_cast<size_t>(nh) * 8);
+    std::vector<double> frac(static_cast<size_t>(nh) * 8);
+    for (int x = 0; x < ax.n_out; ++x) {
+        std::fill(v.begin(), v.end(), 0);
+        std::fill(frac.begin(), frac.end(), 0.0);
+        int64_t sum = 0;
+        for (int t = 0; t < ax.taps; ++t) {
+            const double w = static_cast<double>(ax.w[static_cast<size_t>(x) * ax.taps + t]) * 65536.0;
+            v[t] = static_cast<int64_t>(std::floor(w));
+            frac[t] = w - std::floor(w);
+            sum += v[t];
+        }
+        for (int64_t left = 65536 - sum; left > 0; --left) {  // hand the missing units to the largest remainders
+            int best = 0;
+            for (int t = 1; t < ax.taps; ++t)
+                if (frac[t] > frac[best]) best = t;
+            if (frac[best] <= 0.0) break;
+            ++v[best];
+            frac[best] = -1.0;
+        }
+        for (int t = 0; t < nh * 8; ++t) v[t] = std::min<int64_t>(std::max<int64_t>(v[t], 0), 65535);
+        for (int t = 0; t < nh * 8; t += 2)
+            q[static_cast<size_t>(x) * nh * 4 + t / 2] = static_cast<uint32_t>(v[t]) | (static_cast<uint32_t>(v[t + 1]) << 16);
+    }
+    return q;
+}
+
 }  // namespace agym

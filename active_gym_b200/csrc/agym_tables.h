@@ -36,4 +36,10 @@ AaAxis build_aa_axis(int n_in, int n_out);
 // so the composition is the same linear map (weights multiplied and summed in double).
 AaAxis build_blur_axis(int r, int f);
 
+// The same operator in 16-bit fixed point for IDP.2A (k_observe_flexible_v3's W pass): per output index
+// `halves` groups of 8 weights (taps 0-7, 8-15, ...) starting at xmin, scaled by 2^16 and rounded by largest
+// remainder so that every row sums to 2^16 exactly (a lone weight of 1.0 is stored as 65535); two weights per
+// 32-bit word, low half first.  Error against the float weights: < 2^-16 per tap, zero on constant images.
+std::vector<uint32_t> quantize_axis_q16(const AaAxis &ax, int *halves);
+
 }  // namespace agym

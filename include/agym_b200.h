@@ -165,6 +165,12 @@ AGYM_API int agym_observe_flexible(const agym_plan *plan, const uint8_t *d_ring,
  * h_xmin has n_out entries, h_w has n_out * (*taps) entries (capacity w_capacity floats). */
 AGYM_API int agym_table_cv2(int n_src, int n_dst, int zero_frac_at_border, int32_t *h_s0, int32_t *h_s1, int32_t *h_coef);
 AGYM_API int agym_table_aa(int n_in, int n_out, int32_t *h_xmin, float *h_w, size_t w_capacity, int32_t *taps);
+/* agym_table_blur: the flexible fovea's blur Resize(f) -> Resize(r) along one axis (fov_env.py:276-280) as ONE
+ * banded r x r operator: h_xmin [r], h_w [r][*taps] float weights, and the 16-bit fixed-point form the W pass
+ * of agym_observe_flexible multiplies with, h_q [r][*halves * 8] (weights * 2^16, every row sums to 2^16).
+ * capacity: entries available in h_w and in h_q. */
+AGYM_API int agym_table_blur(int r, int f, int32_t *h_xmin, float *h_w, uint16_t *h_q, size_t capacity, int32_t *taps,
+                             int32_t *halves);
 
 /* Consumer-side convenience: u8 observations -> the reference's normalised value
  * float32(u) / 255 (atari_env.py:75, dmc_env.py:183).  AGYM_DTYPE_F32 is bit-identical to the reference's

@@ -80,3 +80,34 @@ def test_aa_tables_reproduce_the_antialiased_resize(ish, osh):
     t = np.stack([(x[:, xm[i]:xm[i] + ww.shape[1]] * ww[i]).sum(1) for i in range(osh[1])], 1)   # W pass
     y = np.stack([(t[ym[j]:ym[j] + wh.shape[1]] * wh[j][:, None]).sum(0) for j in range(osh[0])], 0)  # H pass
     assert np.abs(y - orc.aa_resize(x, osh)).max() <= 1e-4  # float32 weights vs the float64 oracle, u8 LSB
+
+
+def _blur_axis(r, f):
+    xmin = np.zeros(r, np.int32)
+    w = np.zeros(r * 32, np.float32)
+    q = np.zeros(r * 32, np.uint16)
+    taps, halves = C.c_int32(), C.c_int32()
+    assert _lib.lib().agym_table_blur(r, f, xmin.ctypes.data, w.ctypes.data, q.ctypes.data, w.size,
+                                      C.byref(taps), C.byref(halves)) == 0
+    return xmin, w[:r * taps.value].reshape(r, taps.value), q[:r * halves.value * 8].reshape(r, halves.value * 8)
+
+
+@pytest.mark.parametrize("r", [1, 2, 7, 29, 30, 31, 35, 44, 50, 63, 84])
+def test_blur_tables_compose_the_two_resamples_and_quantise_within_bound(r):
+    """The flexible fovea's blur Resize(30) -> Resize(r) as one banded operator (fov_env.py:276-280): the float table
+    reproduces the oracle's two-step resample, the 16-bit table (what the CUDA W pass multiplies with) sums to 2^16
+    per row and stays within 255 * taps / 2^17 LSB of it on arbitrary u8 rows."""
+    f = 30
+    rng = np.random.default_rng(r)
+    xm, w, q = _blur_axis(r, f)
+    taps = w.shape[1]
+    assert (xm >= 0).all() and (xm + taps <= r).all()
+    x = rng.integers(0, 256, (5, r)).astype(np.float64)
+    want = orc.aa_resize(orc.aa_resize(x, (5, f)), (5, r))          # W axis only: rows are kept (5 -> 5 is the identity)
+    got = np.stack([(x[:, xm[i]:xm[i] + taps] * w[i]).sum(1) for i in range(r)], 1)
+    assert np.abs(got - want).max() <= 1e-4
+    assert (q.astype(np.int64).sum(1) == 65536).all() or (w.max() >= 1.0 - 1e-7)   # a lone 1.0 is stored as 65535
+    assert (q[:, taps:] == 0).all(), "padding taps carry zero weight (they read past the window)"
+    xp = np.concatenate([x, np.zeros((5, 16))], 1)
+    gq = np.stack([(xp[:, xm[i]:xm[i] + q.shape[1]] * q[i].astype(np.float64)).sum(1) for i in range(r)], 1) / 65536.0
+    assert np.abs(gq - want).max() <= 255.0 * max(taps, 2) / 2 ** 17 + 1e-4   # taps == 1: the lone 65535 / 65536
