@@ -378,6 +378,12 @@ int agym_plan_create(const agym_config *cfg, agym_plan **out_plan) {
         }
     };
     spans(cy.s0, cy.s1, d.tma_span_rows);
+    {   // the period-5 row pattern of the standard 210 -> 84 resize (strided tensor copies in the TMA ingest kernel)
+        bool p5 = c.obs_h % 2 == 0 && c.raw_h % 5 == 0 && 5 * (c.obs_h / 2) <= c.raw_h;
+        for (int m = 0; p5 && m < c.obs_h / 2; ++m)
+            p5 = cy.s0[2 * m] == 5 * m && cy.s1[2 * m] == 5 * m + 1 && cy.s0[2 * m + 1] == 5 * m + 3 && cy.s1[2 * m + 1] == 5 * m + 4;
+        d.tma_period5 = p5;
+    }
     if (fast_ingest) {
         d.cx_pair = reinterpret_cast<const int4 *>(base + o_pair);
         d.cy_bs = reinterpret_cast<const int2 *>(base + o_ybs);
@@ -401,6 +407,7 @@ int agym_plan_create(const agym_config *cfg, agym_plan **out_plan) {
     pl->dev_packed.cy_s1 = ip(o_ys1p);
     pl->dev_packed.raw_h = static_cast<int32_t>(used.size());
     spans(ys0p, ys1p, pl->dev_packed.tma_span_rows);
+    pl->dev_packed.tma_period5 = 0;   // packed rows are already gap-free
     *out_plan = pl;
     return AGYM_OK;
 }

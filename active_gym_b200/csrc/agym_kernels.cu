@@ -15,8 +15,11 @@
 #define AGYM_EXPERIMENT 0
 #endif
 
+#include <cuda.h>
+
 #include <algorithm>
 #include <cstdlib>
+#include <cstring>
 
 #include "../../include/agym_b200.h"
 
@@ -483,6 +486,14 @@ __device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gmem_src, u
                  : "memory");
 }
 
+// 4-D tiled tensor copy global -> shared through a CUtensorMap (TMA; SASS: UTMALDG), completing on an mbarrier
+__device__ __forceinline__ void tensor_g2s_4d(void *smem_dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+
 // 1-D bulk copy shared -> global (TMA store; SASS: UBLKCP), tracked by bulk async-groups
 __device__ __forceinline__ void bulk_s2g(void *gmem_dst, const void *smem_src, uint32_t bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_u32(smem_src)),
@@ -512,7 +523,11 @@ __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;"
 constexpr int kIngestThreads = kThreads + 32;
 constexpr int kStages = 2;
 
-template <int RAW_W, int S_W, int CH>  // RAW_W: BYTES per raw row (pixels * CH) when baked in
+// TM: the standard 2.5x vertical scale samples raw rows {5m, 5m+1} (even output rows) and {5m+3, 5m+4} (odd ones)
+// and never row 5m+2.  The frames are then viewed as a 4-D tensor [env][period of 5 rows][row in period][row bytes]
+// and a unit's rows arrive as TWO tiled tensor copies per frame (boxes of 2 rows x R/2 periods at row 0 and at
+// row 3 of the period): the unsampled fifth of every frame never leaves HBM, with as few copies as before.
+template <int RAW_W, int S_W, int CH, bool TM>  // RAW_W: BYTES per raw row (pixels * CH) when baked in
 __global__ void __launch_bounds__(kIngestThreads, 3) k_ingest_atari_tma(const __grid_constant__ DevPlan p,
                                                                         const uint8_t *__restrict__ fa,
                                                                         const uint8_t *__restrict__ fb,
@@ -520,8 +535,11 @@ __global__ void __launch_bounds__(kIngestThreads, 3) k_ingest_atari_tma(const __
                                                                         uint8_t *__restrict__ ring,
                                                                         int32_t *__restrict__ head,
                                                                         float *__restrict__ pcache, int units,
-                                                                        int span_rows) {
-    extern __shared__ __align__(16) uint8_t smem[];
+                                                                        int span_rows,
+                                                                        const __grid_constant__ CUtensorMap tma,
+                                                                        const __grid_constant__ CUtensorMap tmb) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    uint8_t *smem = smem_raw + (TM ? ((128u - (smem_u32(smem_raw) & 127u)) & 127u) : 0u);   // tensor copies land on 128-byte lines
     __shared__ __align__(8) uint64_t full[kStages], empty[kStages];
     constexpr int kEnvWin = 64;
     __shared__ int s_envfl[kEnvWin], s_envhd[kEnvWin];
@@ -530,7 +548,8 @@ __global__ void __launch_bounds__(kIngestThreads, 3) k_ingest_atari_tma(const __
     const int raw_w = RAW_W ? RAW_W : p.raw_w * CH;               // bytes per raw row
     const int S_w = S_W ? S_W : p.S_w;
     const int R = p.S_h / units;                          // output rows per unit
-    const int frame_stride = span_rows * raw_w + 16;      // one frame's staged row span of a unit (+ pad)
+    const int block_bytes = R * raw_w;                    // TM: the R/2 x 2 rows of one tensor copy
+    const int frame_stride = TM ? 2 * block_bytes + 128 : span_rows * raw_w + 16;  // one frame's staged rows of a unit (+ pad)
     const int stage_bytes = (2 * frame_stride + 15) & ~15;
     uint8_t *stages = smem;
     uint8_t *s_frame = stages + kStages * stage_bytes;
@@ -548,9 +567,15 @@ __global__ void __launch_bounds__(kIngestThreads, 3) k_ingest_atari_tma(const __
         mbar_fence_init();
     }
     for (int y = tid; y < p.S_h; y += kIngestThreads) {
-        const int lo = __ldg(p.cy_s0 + (y / R) * R);     // first source row of this row's unit
         const int2 bs = __ldg(p.cy_bs + y);
-        s_row[y] = make_int4((__ldg(p.cy_s0 + y) - lo) * raw_w, (__ldg(p.cy_s1 + y) - lo) * raw_w, bs.x, bs.y);
+        if (TM) {   // even rows of the unit in the first block, odd rows in the second, two staged rows each
+            const int yy = y - (y / R) * R;
+            const int o = ((yy & 1) ? block_bytes : 0) + (yy >> 1) * 2 * raw_w;
+            s_row[y] = make_int4(o, o + raw_w, bs.x, bs.y);
+        } else {
+            const int lo = __ldg(p.cy_s0 + (y / R) * R);     // first source row of this row's unit
+            s_row[y] = make_int4((__ldg(p.cy_s0 + y) - lo) * raw_w, (__ldg(p.cy_s1 + y) - lo) * raw_w, bs.x, bs.y);
+        }
     }
     for (int u = tid; u < units; u += kIngestThreads) {
         const int lo = __ldg(p.cy_s0 + u * R), hi = __ldg(p.cy_s1 + u * R + R - 1);
@@ -578,12 +603,25 @@ __global__ void __launch_bounds__(kIngestThreads, 3) k_ingest_atari_tma(const __
                 const int fl = flags[n];
                 const int2 span = s_span[part];
                 const int nvalid = (fl & AGYM_FLAG_IDLE) ? 0 : __popc(fl & 3);
-                mbar_expect_tx(&full[st], (uint32_t)(nvalid * span.y));
-                if (nvalid) {
-                    uint8_t *dst = stages + st * stage_bytes;
-                    const size_t off = frame_bytes * n + (size_t)span.x * raw_w;
-                    if (fl & AGYM_FLAG_FRAME_A) bulk_g2s(dst, fa + off, span.y, &full[st]);
-                    if (fl & AGYM_FLAG_FRAME_B) bulk_g2s(dst + frame_stride, fb + off, span.y, &full[st]);
+                uint8_t *dst = stages + st * stage_bytes;
+                if (TM) {
+                    mbar_expect_tx(&full[st], (uint32_t)(nvalid * 2 * block_bytes));
+                    const int m0 = (R >> 1) * part;
+                    if (nvalid && (fl & AGYM_FLAG_FRAME_A)) {
+                        tensor_g2s_4d(dst, &tma, &full[st], 0, 0, m0, n);
+                        tensor_g2s_4d(dst + block_bytes, &tma, &full[st], 0, 3, m0, n);
+                    }
+                    if (nvalid && (fl & AGYM_FLAG_FRAME_B)) {
+                        tensor_g2s_4d(dst + frame_stride, &tmb, &full[st], 0, 0, m0, n);
+                        tensor_g2s_4d(dst + frame_stride + block_bytes, &tmb, &full[st], 0, 3, m0, n);
+                    }
+                } else {
+                    mbar_expect_tx(&full[st], (uint32_t)(nvalid * span.y));
+                    if (nvalid) {
+                        const size_t off = frame_bytes * n + (size_t)span.x * raw_w;
+                        if (fl & AGYM_FLAG_FRAME_A) bulk_g2s(dst, fa + off, span.y, &full[st]);
+                        if (fl & AGYM_FLAG_FRAME_B) bulk_g2s(dst + frame_stride, fb + off, span.y, &full[st]);
+                    }
                 }
                 if (++part == units) { part = 0; n += gridDim.x; }
                 if (++st == kStages) { st = 0; ph ^= 1; }
@@ -2306,6 +2344,41 @@ const int g_units = getenv("AGYM_INGEST_UNITS") ? atoi(getenv("AGYM_INGEST_UNITS
 }  // namespace
 
 // --------------------------------------------------------------------------- launchers
+namespace {
+// cuTensorMapEncodeTiled through the runtime's driver entry point (the library does not link libcuda)
+using EncodeTiledFn = CUresult (*)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = [] {
+        void *f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+            f = nullptr;
+        return reinterpret_cast<EncodeTiledFn>(f);
+    }();
+    return fn;
+}
+// frames [N][raw_h][rowb bytes] as [N][raw_h / 5][5][rowb]; box = 2 rows of R/2 consecutive periods of one env
+bool encode_period5(CUtensorMap *m, const uint8_t *frames, int rowb, int raw_h, int N, int R) {
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) return false;
+    CUtensorMapDataType dt = CU_TENSOR_MAP_DATA_TYPE_UINT8;
+    int esz = 1;
+    if (rowb > 256) { dt = CU_TENSOR_MAP_DATA_TYPE_UINT16; esz = 2; }
+    if (rowb > 512) { dt = CU_TENSOR_MAP_DATA_TYPE_UINT32; esz = 4; }
+    if (rowb % (16 * 1) != 0 || rowb / esz > 256 || R % 2 != 0 || R / 2 > 256) return false;
+    const cuuint64_t dims[4] = {(cuuint64_t)(rowb / esz), 5, (cuuint64_t)(raw_h / 5), (cuuint64_t)N};
+    const cuuint64_t strides[3] = {(cuuint64_t)rowb, (cuuint64_t)5 * rowb, (cuuint64_t)raw_h * rowb};
+    const cuuint32_t box[4] = {(cuuint32_t)(rowb / esz), 2, (cuuint32_t)(R / 2), 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    return enc(m, dt, 4, const_cast<uint8_t *>(frames), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+// AGYM_NO_TM=1: contiguous bulk copies instead of the strided tensor copies in the TMA ingest kernel (A/B)
+const bool g_disable_tm = getenv("AGYM_NO_TM") != nullptr;
+}  // namespace
+
 cudaError_t launch_ingest_atari(const DevPlan &p, const uint8_t *fa, const uint8_t *fb, const uint8_t *flags,
                                 uint8_t *ring, int32_t *head, float *pcache, cudaStream_t st) {
     size_t smem = a16(sizeof(int32_t) * 3 * (p.S_w + p.S_h)) + a16(2 * (size_t)2 * p.S_h * p.raw_w);
@@ -2320,8 +2393,15 @@ cudaError_t launch_ingest_atari(const DevPlan &p, const uint8_t *fa, const uint8
     const bool tma_ok = p.raw_c == 1 || (p.raw_c == 3 && p.fast_ingest_rgb);
     if (p.fast_ingest && tma_ok && !g_disable_tma && p.tma_span_rows[ui - 1] > 0) {
         const int units = ui, span_rows = p.tma_span_rows[ui - 1];
-        const size_t stage = a16(2 * ((size_t)span_rows * p.raw_w * p.raw_c + 16));
-        size_t fs = 2 * stage + a16(p.plane + 16) + 16 * (size_t)p.S_h + 8 * (size_t)((units + 1) & ~1);
+        const int rowb = p.raw_w * p.raw_c, R = p.S_h / units;
+        CUtensorMap tma, tmb;
+        std::memset(&tma, 0, sizeof(tma));
+        std::memset(&tmb, 0, sizeof(tmb));
+        const bool tm = p.tma_period5 && !g_disable_tm && R % 2 == 0 && ((size_t)R * rowb) % 128 == 0 &&
+                        (reinterpret_cast<uintptr_t>(fa) & 15) == 0 && (reinterpret_cast<uintptr_t>(fb) & 15) == 0 &&
+                        encode_period5(&tma, fa, rowb, p.raw_h, p.N, R) && encode_period5(&tmb, fb, rowb, p.raw_h, p.N, R);
+        const size_t stage = tm ? a16(2 * (2 * (size_t)R * rowb + 128)) : a16(2 * ((size_t)span_rows * rowb + 16));
+        size_t fs = (tm ? 128 : 0) + 2 * stage + a16(p.plane + 16) + 16 * (size_t)p.S_h + 8 * (size_t)((units + 1) & ~1);
         if (pcache) fs += sizeof(float) * ((size_t)p.S_h * p.p_w + (size_t)p.p_w * 24 + (size_t)p.p_h * p.sq_h.taps + (size_t)p.p_h);
         int dev = 0, sms = 148, occ = 1;
         cudaGetDevice(&dev);
@@ -2331,13 +2411,20 @@ cudaError_t launch_ingest_atari(const DevPlan &p, const uint8_t *fa, const uint8
         if ((e = set_smem(k_ingest_atari_tma<__VA_ARGS__>, fs)) != cudaSuccess) return e;                           \
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_ingest_atari_tma<__VA_ARGS__>, kIngestThreads, fs);   \
         k_ingest_atari_tma<__VA_ARGS__><<<std::min(p.N, sms * std::max(occ, 1)), kIngestThreads, fs, st>>>(         \
-            p, fa, fb, flags, ring, head, pcache, units, span_rows);                                                \
+            p, fa, fb, flags, ring, head, pcache, units, span_rows, tma, tmb);                                      \
     }
+        const bool std_geom = p.raw_w == 160 && p.S_w == 84;
         if (p.raw_c == 3) {
-            if (p.raw_w == 160 && p.S_w == 84) AGYM_LAUNCH_TMA(480, 84, 3)
-            else AGYM_LAUNCH_TMA(0, 0, 3)
-        } else if (p.raw_w == 160 && p.S_w == 84) AGYM_LAUNCH_TMA(160, 84, 1)
-        else AGYM_LAUNCH_TMA(0, 0, 1)
+            if (std_geom && tm) AGYM_LAUNCH_TMA(480, 84, 3, true)
+            else if (std_geom) AGYM_LAUNCH_TMA(480, 84, 3, false)
+            else if (tm) AGYM_LAUNCH_TMA(0, 0, 3, true)
+            else AGYM_LAUNCH_TMA(0, 0, 3, false)
+        } else {
+            if (std_geom && tm) AGYM_LAUNCH_TMA(160, 84, 1, true)
+            else if (std_geom) AGYM_LAUNCH_TMA(160, 84, 1, false)
+            else if (tm) AGYM_LAUNCH_TMA(0, 0, 1, true)
+            else AGYM_LAUNCH_TMA(0, 0, 1, false)
+        }
 #undef AGYM_LAUNCH_TMA
         return cudaGetLastError();
     }

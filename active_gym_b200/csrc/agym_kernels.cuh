@@ -52,6 +52,7 @@ struct DevPlan {
     // and per output row {b0 << 16, b1 << 16} (atari_env.py:74 fixed-point bilinear, dp2a form)
     int32_t fast_ingest;
     int32_t tma_span_rows[8];  // TMA ingest: largest source-row span of a unit when an env is cut into 1..8 units (0 = n/a)
+    int32_t tma_period5;       // vertical scale 2.5: output row 2m samples raw rows {5m, 5m+1}, row 2m+1 {5m+3, 5m+4}
     int32_t fast_ingest_rgb;   // 3-channel frames: every column pair's four source pixels lie among s0 .. s0 + 3
     const int4 *cx_pair;    // [S_w / 2]
     const int2 *cy_bs;      // [S_h]
