@@ -521,13 +521,12 @@ __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;"
 // RAW_W / S_W > 0 bake the strides of the standard geometry (210x160 -> 84x84) into the
 // instruction immediates; 0 = take them from the plan.
 constexpr int kIngestThreads = kThreads + 32;
-constexpr int kStages = 2;
 
 // TM: the standard 2.5x vertical scale samples raw rows {5m, 5m+1} (even output rows) and {5m+3, 5m+4} (odd ones)
 // and never row 5m+2.  The frames are then viewed as a 4-D tensor [env][period of 5 rows][row in period][row bytes]
 // and a unit's rows arrive as TWO tiled tensor copies per frame (boxes of 2 rows x R/2 periods at row 0 and at
 // row 3 of the period): the unsampled fifth of every frame never leaves HBM, with as few copies as before.
-template <int RAW_W, int S_W, int CH, bool TM>  // RAW_W: BYTES per raw row (pixels * CH) when baked in
+template <int RAW_W, int S_W, int CH, bool TM, int NS>  // RAW_W: BYTES per raw row (pixels * CH) when baked in; NS: stages
 __global__ void __launch_bounds__(kIngestThreads, 3) k_ingest_atari_tma(const __grid_constant__ DevPlan p,
                                                                         const uint8_t *__restrict__ fa,
                                                                         const uint8_t *__restrict__ fb,
@@ -540,7 +539,7 @@ __global__ void __launch_bounds__(kIngestThreads, 3) k_ingest_atari_tma(const __
                                                                         const __grid_constant__ CUtensorMap tmb) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     uint8_t *smem = smem_raw + (TM ? ((128u - (smem_u32(smem_raw) & 127u)) & 127u) : 0u);   // tensor copies land on 128-byte lines
-    __shared__ __align__(8) uint64_t full[kStages], empty[kStages];
+    __shared__ __align__(8) uint64_t full[NS], empty[NS];
     constexpr int kEnvWin = 64;
     __shared__ int s_envfl[kEnvWin], s_envhd[kEnvWin];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -552,7 +551,7 @@ __global__ void __launch_bounds__(kIngestThreads, 3) k_ingest_atari_tma(const __
     const int frame_stride = TM ? 2 * block_bytes + 128 : span_rows * raw_w + 16;  // one frame's staged rows of a unit (+ pad)
     const int stage_bytes = (2 * frame_stride + 15) & ~15;
     uint8_t *stages = smem;
-    uint8_t *s_frame = stages + kStages * stage_bytes;
+    uint8_t *s_frame = stages + NS * stage_bytes;
     float *s_t1 = reinterpret_cast<float *>(s_frame + align16(p.plane + 16));
     int4 *s_row = reinterpret_cast<int4 *>(s_t1 + (pcache ? p.S_h * p.p_w : 0));  // [S_h] {ofs0, ofs1, b0<<16, b1<<16}
     int2 *s_span = reinterpret_cast<int2 *>(s_row + p.S_h);                       // [units] {first row, bytes}
@@ -563,7 +562,7 @@ __global__ void __launch_bounds__(kIngestThreads, 3) k_ingest_atari_tma(const __
     const size_t frame_bytes = (size_t)p.raw_h * raw_w;
 
     if (tid == 0) {
-        for (int i = 0; i < kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], kThreads / 32); }
+        for (int i = 0; i < NS; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], kThreads / 32); }
         mbar_fence_init();
     }
     for (int y = tid; y < p.S_h; y += kIngestThreads) {
@@ -599,7 +598,7 @@ __global__ void __launch_bounds__(kIngestThreads, 3) k_ingest_atari_tma(const __
         if (lane == 0) {
             int n = blockIdx.x, part = 0, st = 0, ph = 1;  // ph: parity of the empty-barrier phase to wait for
             for (int it = 0; it < my_units; ++it) {
-                if (it >= kStages) mbar_wait<true>(&empty[st], ph);
+                if (it >= NS) mbar_wait<true>(&empty[st], ph);
                 const int fl = flags[n];
                 const int2 span = s_span[part];
                 const int nvalid = (fl & AGYM_FLAG_IDLE) ? 0 : __popc(fl & 3);
@@ -624,7 +623,7 @@ __global__ void __launch_bounds__(kIngestThreads, 3) k_ingest_atari_tma(const __
                     }
                 }
                 if (++part == units) { part = 0; n += gridDim.x; }
-                if (++st == kStages) { st = 0; ph ^= 1; }
+                if (++st == NS) { st = 0; ph ^= 1; }
             }
         }
         return;
@@ -736,7 +735,7 @@ __global__ void __launch_bounds__(kIngestThreads, 3) k_ingest_atari_tma(const __
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[st]);  // this warp is done with the stage
-        if (++st == kStages) { st = 0; ph ^= 1; }
+        if (++st == NS) { st = 0; ph ^= 1; }
         if (++part < units) continue;
         part = 0;
         const int n_done = n;
@@ -2375,6 +2374,8 @@ bool encode_period5(CUtensorMap *m, const uint8_t *frames, int rowb, int raw_h, 
     return enc(m, dt, 4, const_cast<uint8_t *>(frames), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
+// AGYM_INGEST_STAGES=3: three stages in the TMA ingest ring (tuning)
+const int g_stages = getenv("AGYM_INGEST_STAGES") ? atoi(getenv("AGYM_INGEST_STAGES")) : 0;
 // AGYM_NO_TM=1: contiguous bulk copies instead of the strided tensor copies in the TMA ingest kernel (A/B)
 const bool g_disable_tm = getenv("AGYM_NO_TM") != nullptr;
 }  // namespace
@@ -2401,7 +2402,10 @@ cudaError_t launch_ingest_atari(const DevPlan &p, const uint8_t *fa, const uint8
                         (reinterpret_cast<uintptr_t>(fa) & 15) == 0 && (reinterpret_cast<uintptr_t>(fb) & 15) == 0 &&
                         encode_period5(&tma, fa, rowb, p.raw_h, p.N, R) && encode_period5(&tmb, fb, rowb, p.raw_h, p.N, R);
         const size_t stage = tm ? a16(2 * (2 * (size_t)R * rowb + 128)) : a16(2 * ((size_t)span_rows * rowb + 16));
-        size_t fs = (tm ? 128 : 0) + 2 * stage + a16(p.plane + 16) + 16 * (size_t)p.S_h + 8 * (size_t)((units + 1) & ~1);
+        const bool std_geom = p.raw_w == 160 && p.S_w == 84;
+        // stages of the shared-memory ring: the gap-free gray stages are small enough for three at 3 CTAs per SM
+        const int ns = (tm && std_geom && (g_stages ? g_stages == 3 : p.raw_c == 1)) ? 3 : 2;
+        size_t fs = (tm ? 128 : 0) + ns * stage + a16(p.plane + 16) + 16 * (size_t)p.S_h + 8 * (size_t)((units + 1) & ~1);
         if (pcache) fs += sizeof(float) * ((size_t)p.S_h * p.p_w + (size_t)p.p_w * 24 + (size_t)p.p_h * p.sq_h.taps + (size_t)p.p_h);
         int dev = 0, sms = 148, occ = 1;
         cudaGetDevice(&dev);
@@ -2413,17 +2417,18 @@ cudaError_t launch_ingest_atari(const DevPlan &p, const uint8_t *fa, const uint8
         k_ingest_atari_tma<__VA_ARGS__><<<std::min(p.N, sms * std::max(occ, 1)), kIngestThreads, fs, st>>>(         \
             p, fa, fb, flags, ring, head, pcache, units, span_rows, tma, tmb);                                      \
     }
-        const bool std_geom = p.raw_w == 160 && p.S_w == 84;
         if (p.raw_c == 3) {
-            if (std_geom && tm) AGYM_LAUNCH_TMA(480, 84, 3, true)
-            else if (std_geom) AGYM_LAUNCH_TMA(480, 84, 3, false)
-            else if (tm) AGYM_LAUNCH_TMA(0, 0, 3, true)
-            else AGYM_LAUNCH_TMA(0, 0, 3, false)
+            if (std_geom && tm && ns == 3) AGYM_LAUNCH_TMA(480, 84, 3, true, 3)
+            else if (std_geom && tm) AGYM_LAUNCH_TMA(480, 84, 3, true, 2)
+            else if (std_geom) AGYM_LAUNCH_TMA(480, 84, 3, false, 2)
+            else if (tm) AGYM_LAUNCH_TMA(0, 0, 3, true, 2)
+            else AGYM_LAUNCH_TMA(0, 0, 3, false, 2)
         } else {
-            if (std_geom && tm) AGYM_LAUNCH_TMA(160, 84, 1, true)
-            else if (std_geom) AGYM_LAUNCH_TMA(160, 84, 1, false)
-            else if (tm) AGYM_LAUNCH_TMA(0, 0, 1, true)
-            else AGYM_LAUNCH_TMA(0, 0, 1, false)
+            if (std_geom && tm && ns == 3) AGYM_LAUNCH_TMA(160, 84, 1, true, 3)
+            else if (std_geom && tm) AGYM_LAUNCH_TMA(160, 84, 1, true, 2)
+            else if (std_geom) AGYM_LAUNCH_TMA(160, 84, 1, false, 2)
+            else if (tm) AGYM_LAUNCH_TMA(0, 0, 1, true, 2)
+            else AGYM_LAUNCH_TMA(0, 0, 1, false, 2)
         }
 #undef AGYM_LAUNCH_TMA
         return cudaGetLastError();
