@@ -10,12 +10,13 @@ import os
 import shutil
 import subprocess
 import sys
+from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "lib", "libagym_b200.so")
-SOURCES = ["agym_kernels.cu", "agym_abi.cu", "agym_tables.cpp"]
-HEADERS = ["agym_kernels.cuh", "agym_tables.h", os.path.join("..", "..", "include", "agym_b200.h")]
+SOURCES = ["agym_ingest.cu", "agym_observe.cu", "agym_flexible.cu", "agym_misc.cu", "agym_abi.cu", "agym_tables.cpp"]
+HEADERS = ["agym_kernels.cuh", "agym_device.cuh", "agym_tables.h", os.path.join("..", "..", "include", "agym_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC,-fvisibility=hidden", "-shared",
@@ -40,13 +41,30 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return OUT
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + \
-          [os.path.join(CSRC, f) for f in SOURCES]
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if verbose or r.returncode != 0:
-        sys.stderr.write(r.stdout + r.stderr)
-    if r.returncode != 0:
+    objdir = os.path.join(HERE, "lib", "obj")
+    os.makedirs(objdir, exist_ok=True)
+    compile_flags = [f for f in NVCC_FLAGS if f != "-shared"] + (["-Xptxas", "-v"] if verbose else [])
+
+    def compile_one(src: str):
+        obj = os.path.join(objdir, os.path.splitext(src)[0] + ".o")
+        cmd = [_nvcc()] + compile_flags + ["-c", "-o", obj, os.path.join(CSRC, src)]
+        return obj, subprocess.run(cmd, capture_output=True, text=True)
+
+    # one translation unit per kernel family: compiled side by side, then linked into the in-tree .so
+    with ThreadPoolExecutor(max_workers=len(SOURCES)) as pool:
+        results = list(pool.map(compile_one, SOURCES))
+    failed = False
+    for _, r in results:
+        if verbose or r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+        failed = failed or r.returncode != 0
+    if failed:
         raise RuntimeError("nvcc failed building libagym_b200.so")
+    link = subprocess.run([_nvcc()] + NVCC_FLAGS + ["-o", OUT] + [o for o, _ in results], capture_output=True, text=True)
+    if verbose or link.returncode != 0:
+        sys.stderr.write(link.stdout + link.stderr)
+    if link.returncode != 0:
+        raise RuntimeError("nvcc failed linking libagym_b200.so")
     return OUT
 
 

@@ -1,4 +1,4 @@
-// Device-side parameter blocks and launcher prototypes shared by agym_kernels.cu (device
+// Device-side parameter blocks and launcher prototypes shared by the kernel translation units agym_{ingest,observe,flexible,misc}.cu (device
 // code + launchers) and agym_abi.cu (plan management + the extern "C" surface).
 #pragma once
 #include <cstdint>

@@ -1,0 +1,87 @@
+// sm_100a kernels: consumer-side normalisation and the synthetic frame generator.
+#include "agym_device.cuh"
+
+namespace agym {
+
+namespace {
+
+// ---------------------------------------------------------------------------- normalise
+// The reference hands the agent float32(u) / 255 (atari_env.py:75, dmc_env.py:183).  Consumer-side
+// convenience: u8 observations -> normalised f32 (bit-identical to the reference's value: IEEE
+// division), f16 or bf16, 16 pixels per thread, 16-byte loads and stores.
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+template <int DT>  // 0 f32, 1 f16, 2 bf16
+__global__ void k_normalize(const uint4 *__restrict__ src, void *__restrict__ dst, size_t n_vec) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n_vec; i += (size_t)gridDim.x * blockDim.x) {
+        const uint4 v = ld_stream128(src + i);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        float f[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) f[j] = __fdiv_rn((float)((w[j >> 2] >> (8 * (j & 3))) & 0xffu), 255.f);
+        if (DT == 0) {
+            float4 *o = reinterpret_cast<float4 *>(dst) + 4 * i;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) o[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+        } else {
+            uint32_t h[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                if (DT == 1) {
+                    const __half2 t = __floats2half2_rn(f[2 * j], f[2 * j + 1]);
+                    h[j] = *reinterpret_cast<const uint32_t *>(&t);
+                } else {
+                    const __nv_bfloat162 t = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+                    h[j] = *reinterpret_cast<const uint32_t *>(&t);
+                }
+            }
+            uint4 *o = reinterpret_cast<uint4 *>(dst) + 2 * i;
+            o[0] = make_uint4(h[0], h[1], h[2], h[3]);
+            o[1] = make_uint4(h[4], h[5], h[6], h[7]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------ synth
+__global__ void k_synth(uint4 *dst, size_t n_vec, uint64_t seed) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n_vec; i += (size_t)gridDim.x * blockDim.x) {
+        uint64_t z = seed + i * 0x9E3779B97F4A7C15ull;
+        uint32_t o[4];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            z += 0x9E3779B97F4A7C15ull;
+            uint64_t x = z;
+            x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+            x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+            x ^= x >> 31;
+            o[2 * j] = (uint32_t)x; o[2 * j + 1] = (uint32_t)(x >> 32);
+        }
+        dst[i] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+}
+
+
+}  // namespace
+
+// --------------------------------------------------------------------------- launchers
+cudaError_t launch_normalize(const uint8_t *src, size_t n, int dtype, void *dst, cudaStream_t st) {
+    const size_t n_vec = n / 16;
+    if (n_vec == 0) return cudaSuccess;
+    const int blocks = (int)std::min<size_t>((n_vec + 255) / 256, 148 * 16);
+    const uint4 *s4 = reinterpret_cast<const uint4 *>(src);
+    if (dtype == 0) k_normalize<0><<<blocks, 256, 0, st>>>(s4, dst, n_vec);
+    else if (dtype == 1) k_normalize<1><<<blocks, 256, 0, st>>>(s4, dst, n_vec);
+    else k_normalize<2><<<blocks, 256, 0, st>>>(s4, dst, n_vec);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_synth(uint8_t *dst, size_t n, uint64_t seed, cudaStream_t st) {
+    const size_t n_vec = n / 16;
+    if (n_vec == 0) return cudaSuccess;
+    const int blocks = (int)((n_vec + 255) / 256 < 148 * 8 ? (n_vec + 255) / 256 : 148 * 8);
+    k_synth<<<blocks, 256, 0, st>>>(reinterpret_cast<uint4 *>(dst), n_vec, seed);
+    return cudaGetLastError();
+}
+
+
+}  // namespace agym

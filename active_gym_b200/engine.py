@@ -3,7 +3,7 @@ environments (frame-stack ring, fovea location / resolution, peripheral cache) a
 tensors and issues the sm_100a kernels through the C ABI (``include/agym_b200.h``).
 
 PyTorch is used here for device memory and streams only; all arithmetic is in
-``csrc/agym_kernels.cu``.  There is no CPU fallback.
+``csrc/agym_{ingest,observe,flexible,misc}.cu``.  There is no CPU fallback.
 """
 from __future__ import annotations
 
