@@ -111,3 +111,16 @@ def test_blur_tables_compose_the_two_resamples_and_quantise_within_bound(r):
     xp = np.concatenate([x, np.zeros((5, 16))], 1)
     gq = np.stack([(xp[:, xm[i]:xm[i] + q.shape[1]] * q[i].astype(np.float64)).sum(1) for i in range(r)], 1) / 65536.0
     assert np.abs(gq - want).max() <= 255.0 * max(taps, 2) / 2 ** 17 + 1e-4   # taps == 1: the lone 65535 / 65536
+
+
+def test_standard_vertical_resize_never_samples_every_fifth_raw_row():
+    """cv2.resize 210 -> 84 (atari_env.py:74): output row 2m reads raw rows {5m, 5m+1}, row 2m+1 reads {5m+3, 5m+4};
+    row 5m+2 is never read.  The TMA ingest kernel's strided tensor copies rely on this pattern (the plan re-checks
+    it on its own tables before enabling them) and on the two vertical weight pairs it implies."""
+    s0, s1, b0, b1 = _cv2_axis(210, 84, False)
+    m = np.arange(42)
+    assert np.array_equal(s0[0::2], 5 * m) and np.array_equal(s1[0::2], 5 * m + 1)
+    assert np.array_equal(s0[1::2], 5 * m + 3) and np.array_equal(s1[1::2], 5 * m + 4)
+    used = np.union1d(s0, s1)
+    assert len(used) == 168 and not np.any(used % 5 == 2)
+    assert set(zip(b0[0::2], b1[0::2])) == {(512, 1536)} and set(zip(b0[1::2], b1[1::2])) == {(1536, 512)}
