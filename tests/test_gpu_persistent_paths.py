@@ -155,6 +155,35 @@ def test_flexible_fast_path_many_envs(variant, pad, n):
         assert np.array_equal(got[sharp], want[sharp])
 
 
+@pytest.mark.parametrize("K,fov", [(3, (30, 30)), (2, (24, 40)), (5, (30, 30))])
+def test_flexible_v3_other_stack_depths_and_fovea_shapes(K, fov):
+    """DMC-style K = 3, K = 2 / 5 and a non-square fovea (blur decided by rows only, fov_env.py:286) through the
+    persistent flexible kernel: the shared-memory budget, the frame groups of the W/H passes and the ring order
+    depend on K."""
+    rng = np.random.default_rng(100 + K)
+    n = 333
+    p = _path(n, K, fov_size=fov, sensory_action_mode="absolute")
+    ring, head = orc.new_state(n, K, S)
+    for step in range(K + 2):
+        fa, fb = _frames(rng, n), _frames(rng, n)
+        fl = np.full(n, 5 if step == 0 else 3, np.uint8)
+        p.ingest_atari(fa, fb, fl)
+        orc.ingest_atari(fa, fb, fl, ring, head)
+    loc = np.zeros((n, 2), np.int32)
+    res = np.tile(np.array([fov], np.int32), (n, 1))
+    p.observe_flexible(None, variant="mask", ctrl="reset")
+    for step in range(3):
+        atype = rng.integers(0, 2, n).astype(np.int32)
+        a = np.where(atype[:, None] == 1, rng.integers(1, 85, (n, 2)), rng.uniform(-5, 90, (n, 2))).astype(np.float64)
+        orc.update_loc(a, loc, obs_size=S, fov_size=fov, atype=atype, res=res)
+        got = _np(p.observe_flexible(a, atype, variant="mask")).astype(np.float64)
+        want = orc.observe_flexible(ring, head, loc, res, fov, variant="mask")
+        assert np.array_equal(_np(p.loc), loc) and np.array_equal(_np(p.res), res), step
+        assert np.abs(got - want).max() <= TOL, step
+        sharp = res[:, 0] <= fov[0]
+        assert np.array_equal(got[sharp], want[sharp])
+
+
 def test_host_pipeline_shards_equal_unsharded_path():
     from active_gym_b200.hostpipe import HostPipelinedEnv
     rng = np.random.default_rng(9)
