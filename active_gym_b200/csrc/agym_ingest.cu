@@ -270,7 +270,7 @@ constexpr int kIngestThreads = kThreads + 32;
 // and never row 5m+2.  The frames are then viewed as a 4-D tensor [env][period of 5 rows][row in period][row bytes]
 // and a unit's rows arrive as TWO tiled tensor copies per frame (boxes of 2 rows x R/2 periods at row 0 and at
 // row 3 of the period): the unsampled fifth of every frame never leaves HBM, with as few copies as before.
-template <int RAW_W, int S_W, int CH, bool TM, int NS>  // RAW_W: BYTES per raw row (pixels * CH) when baked in; NS: stages
+template <int RAW_W, int S_W, int CH, bool TM, int NS, int ROWS = 0>  // RAW_W: BYTES per raw row (pixels * CH) when baked in; NS: stages; ROWS: rows per segment if fixed
 __global__ void __launch_bounds__(kIngestThreads, 3) k_ingest_atari_tma(const __grid_constant__ DevPlan p,
                                                                         const uint8_t *__restrict__ fa,
                                                                         const uint8_t *__restrict__ fb,
@@ -444,9 +444,7 @@ __global__ void __launch_bounds__(kIngestThreads, 3) k_ingest_atari_tma(const __
             const int4 *rw = s_row + part * R + yy_begin;
             uint8_t *o = s_frame + (part * R + yy_begin) * S_w + 2 * pi;
             if ((fl & 3) == 3) {  // both frames (the steady state)
-#pragma unroll 2
-                for (int yy = yy_begin; yy < yy_end; ++yy, ++rw, o += S_w) {
-                    const int4 t = *rw;
+                auto row_both = [&](const int4 t, uint8_t *dst) {
                     const uint8_t *ra = base + t.x, *rb = base + t.y;
                     // max of the two frames taken before the final (x + 2) >> 2, which is monotone; the
                     // result cannot exceed 255 (b0 + b1 = 2048, h >> 4 <= 32640), so cv2's saturate is a no-op
@@ -459,7 +457,14 @@ __global__ void __launch_bounds__(kIngestThreads, 3) k_ingest_atari_tma(const __
                         m0 = max(m0, __umulhi((uint32_t)t.z, h00 >> 4) + __umulhi((uint32_t)t.w, h10 >> 4));
                         m1 = max(m1, __umulhi((uint32_t)t.z, h01 >> 4) + __umulhi((uint32_t)t.w, h11 >> 4));
                     }
-                    *reinterpret_cast<uint16_t *>(o) = (uint16_t)(((m0 + 2u) >> 2) | (((m1 + 2u) >> 2) << 8));
+                    *reinterpret_cast<uint16_t *>(dst) = (uint16_t)(((m0 + 2u) >> 2) | (((m1 + 2u) >> 2) << 8));
+                };
+                if (ROWS > 0) {   // every row segment has exactly ROWS rows: no loop bookkeeping, no odd-row remainder
+#pragma unroll
+                    for (int r = 0; r < ROWS; ++r) row_both(rw[r], o + r * S_w);
+                } else {
+#pragma unroll 2
+                    for (int yy = yy_begin; yy < yy_end; ++yy, ++rw, o += S_w) row_both(*rw, o);
                 }
             } else {  // resets / early game-over: one frame or none
                 for (int yy = yy_begin; yy < yy_end; ++yy, ++rw, o += S_w) {
@@ -722,6 +727,8 @@ bool encode_period5(CUtensorMap *m, const uint8_t *frames, int rowb, int raw_h, 
 }
 // AGYM_INGEST_STAGES=3: three stages in the TMA ingest ring (tuning)
 const int g_stages = getenv("AGYM_INGEST_STAGES") ? atoi(getenv("AGYM_INGEST_STAGES")) : 0;
+// AGYM_NO_ROWS=1: runtime row loop in the gray tensor-copy ingest (A/B)
+const bool g_no_rows = getenv("AGYM_NO_ROWS") != nullptr;
 // AGYM_NO_TM=1: contiguous bulk copies instead of the strided tensor copies in the TMA ingest kernel (A/B)
 const bool g_disable_tm = getenv("AGYM_NO_TM") != nullptr;
 }  // namespace
@@ -786,6 +793,7 @@ cudaError_t launch_ingest_atari(const DevPlan &p, const uint8_t *fa, const uint8
             else AGYM_LAUNCH_TMA(0, 0, 3, false, 2)
         } else {
             if (std_geom && tm && ns == 3) AGYM_LAUNCH_TMA(160, 84, 1, true, 3)
+            else if (std_geom && tm && units == 2 && p.S_h == 84 && !g_no_rows) AGYM_LAUNCH_TMA(160, 84, 1, true, 2, 7)
             else if (std_geom && tm) AGYM_LAUNCH_TMA(160, 84, 1, true, 2)
             else if (std_geom) AGYM_LAUNCH_TMA(160, 84, 1, false, 2)
             else if (tm) AGYM_LAUNCH_TMA(0, 0, 1, true, 2)
