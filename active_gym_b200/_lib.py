@@ -12,7 +12,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("AGYM_LIB") or os.path.join(_HERE, "lib", "libagym_b200.so")  # AGYM_LIB: timing experiments only
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 # status codes / flags (mirrors of the header's macros)
 OK = 0
@@ -20,13 +20,14 @@ FLAG_FRAME_A, FLAG_FRAME_B, FLAG_HARD_RESET, FLAG_IDLE = 1, 2, 4, 8
 FOV_APPLY, FOV_RESET, FOV_KEEP = 0, 1, 2
 OUT_CROP, OUT_MASK, OUT_RESIZE_FULL = 0, 1, 2
 ATYPE_FOV_LOC, ATYPE_FOV_RES = 0, 1
+ERR_RES_RANGE, ERR_RES_FRACTION = 1, 2
 
 # the symbols include/agym_b200.h declares; tests check that the .so exports every one
 EXPORTS = (
     "agym_abi_version", "agym_status_string", "agym_plan_create", "agym_plan_destroy",
     "agym_plan_ring_bytes", "agym_plan_pcache_bytes", "agym_ingest_atari", "agym_ingest_dmc",
     "agym_stack", "agym_observe_fixed", "agym_observe_peripheral", "agym_observe_flexible",
-    "agym_synth_frames", "agym_table_cv2", "agym_table_aa", "agym_table_blur", "agym_normalize", "agym_plan_used_rows", "agym_ingest_atari_packed",
+    "agym_synth_frames", "agym_table_cv2", "agym_table_aa", "agym_table_blur", "agym_normalize", "agym_plan_used_rows", "agym_ingest_atari_packed", "agym_record_step",
 )
 
 
@@ -69,7 +70,8 @@ def lib() -> C.CDLL:
     L.agym_stack.argtypes = [vp] * 5
     L.agym_observe_fixed.argtypes = [vp, vp, vp, vp, vp, vp, i32, vp, vp]
     L.agym_observe_peripheral.argtypes = [vp] * 9
-    L.agym_observe_flexible.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp, vp]
+    L.agym_observe_flexible.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp, vp, vp]
+    L.agym_record_step.argtypes = [i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     L.agym_synth_frames.argtypes = [vp, sz, u64, vp]
     L.agym_normalize.argtypes = [vp, sz, i32, vp, vp]
     L.agym_table_cv2.argtypes = [i32, i32, i32, vp, vp, vp]

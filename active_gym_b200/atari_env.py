@@ -13,7 +13,8 @@ import numpy as np
 import torch
 
 from . import _lib
-from .engine import LUMA_RGB, ObservationPath
+from .engine import LUMA_RGB
+from .pipeline import PipelinedPath
 from .spaces import Box, Discrete, Env
 
 
@@ -38,10 +39,16 @@ class AtariEnvArgs:
             self.__setattr__(k, v)
 
 
-def _path_from_args(args, num_envs, raw_shape, luma, device) -> ObservationPath:
+def _path_from_args(args, num_envs, raw_shape, luma, device, host_source: bool) -> PipelinedPath:
+    """The per-GPU engine of an env batch.  ``args.shards`` (default: 8 for host frame sources, whose copies
+    should overlap the kernels; 1 for device-resident sources) cuts the batch into env-index shards with their own
+    streams (pipeline.PipelinedPath)."""
     fov = getattr(args, "fov_size", None)
-    return ObservationPath(
-        num_envs, args.frame_stack, tuple(args.obs_size), raw_shape, luma=luma,
+    shards = getattr(args, "shards", None)
+    if shards is None:
+        shards = 8 if host_source and num_envs >= 64 else 1
+    return PipelinedPath(
+        num_envs, args.frame_stack, tuple(args.obs_size), raw_shape, shards=shards, luma=luma,
         fov_size=tuple(fov) if fov is not None else None,
         fov_init_loc=getattr(args, "fov_init_loc", (0, 0)),
         sensory_action_mode=getattr(args, "sensory_action_mode", "absolute"),
@@ -50,7 +57,48 @@ def _path_from_args(args, num_envs, raw_shape, luma, device) -> ObservationPath:
         cache_peripheral=getattr(args, "cache_peripheral", True))
 
 
-class AtariVecEnv(Env):
+class _VecBase(Env):
+    """What AtariVecEnv and DMCVecEnv share: the frame source below, the pipelined engine, and the asynchronous
+    protocol ``step_async`` / ``step_wait`` (``step`` = both), which lets a caller run two env groups
+    alternately — the simulators of one group step on the host while the other group's frames are copied and
+    transformed on the GPU."""
+
+    def _init_engine(self, args, num_envs, source, luma, device):
+        self.args = args
+        self.num_envs = int(num_envs)
+        self.frame_stack = args.frame_stack
+        self.action_repeat = args.action_repeat
+        self.obs_size = tuple(args.obs_size)
+        self.clip_reward = args.clip_reward
+        self.source = source
+        host_source = not hasattr(source, "device")
+        self.path = _path_from_args(args, self.num_envs, tuple(source.raw_shape), luma,
+                                    device or getattr(args, "device", None), host_source)
+        self.device = self.path.device
+        self.host_obs = bool(getattr(args, "host_obs", False))
+        if host_source and hasattr(source, "set_used_rows") and self.path.run is not None:
+            source.set_used_rows(self.path.used_rows)   # only the sampled raw rows cross PCIe, as one block per shard
+        self.observation_space = Box(low=-1., high=1., shape=(self.frame_stack,) + self.obs_size, dtype=np.float32)
+        self._pending = None
+
+    def _frames_enqueued(self):
+        """Tells the source that the copies reading its current staging set are in the streams."""
+        if hasattr(self.source, "frames_consumed"):
+            self.source.frames_consumed(self.path.record_events())
+
+    def step(self, action, return_state=True):
+        self.step_async(action)
+        return self.step_wait(return_state=return_state)
+
+    def close(self):
+        if hasattr(self.source, "close"):
+            self.source.close()
+
+    def render(self, mode="rgb_array", obs_size=None):
+        raise NotImplementedError("recording/rendering is outside the observation hot path (SURVEY.md §2 row 2)")
+
+
+class AtariVecEnv(_VecBase):
     """N Atari environments; observation = (N, K, S_h, S_w) uint8 CUDA tensor.
 
     Replaces AtariEnv (atari_env.py:41-172) for a batch.  ``source`` supplies the simulators
@@ -59,38 +107,38 @@ class AtariVecEnv(Env):
     """
 
     def __init__(self, args, num_envs: int = 1, source=None, device=None):
-        self.args = args
-        self.num_envs = int(num_envs)
-        self.frame_stack = args.frame_stack
-        self.action_repeat = args.action_repeat
-        self.obs_size = tuple(args.obs_size)
-        self.clip_reward = args.clip_reward
         self.training = True
         if source is None:
             from .sources import ALEPool
-            source = ALEPool(args, self.num_envs, workers=getattr(args, "sim_workers", 1))
-        self.source = source
-        self.path = _path_from_args(args, self.num_envs, tuple(source.raw_shape),
-                                    getattr(args, "luma", LUMA_RGB), device or getattr(args, "device", None))
-        self.device = self.path.device
+            source = ALEPool(args, int(num_envs), workers=getattr(args, "sim_workers", 1))
+        self._init_engine(args, num_envs, source, getattr(args, "luma", LUMA_RGB), device)
         self.action_space = Discrete(source.n_actions)
-        self.observation_space = Box(low=-1., high=1., shape=(self.frame_stack,) + self.obs_size, dtype=np.float32)
         self.reward_range = (-float("inf"), float("inf"))
 
     def _info(self, raw_reward):
         return {"raw_reward": raw_reward}  # atari_env.py:77-78
 
+    def _ingest(self, fa, fb, flags):
+        self.path.ingest_atari(fa, fb, flags, packed=bool(getattr(self.source, "packed_rows", False)))
+        self._frames_enqueued()
+
     def reset(self, seed=None, options=None, mask=None, return_state=True):
         """atari_env.py:84-117.  ``mask`` (N,) bool selects the envs to reset (default: all)."""
         fa, fb, flags = self.source.reset(mask)
-        self.path.ingest_atari(fa, fb, flags)
+        self._ingest(fa, fb, flags)
         state = self.path.stack() if return_state else None
         return state, self._info(np.zeros(self.num_envs))
 
-    def step(self, action, return_state=True):
-        """atari_env.py:119-148."""
+    def step_async(self, action):
+        """atari_env.py:119-133: steps the simulators (host) and enqueues copy + ingest; returns at once."""
         fa, fb, flags, reward, done = self.source.step(action)
-        self.path.ingest_atari(fa, fb, flags)
+        self._ingest(fa, fb, flags)
+        self._pending = (reward, done)
+
+    def step_wait(self, return_state=True):
+        """atari_env.py:134-148."""
+        reward, done = self._pending
+        self._pending = None
         state = self.path.stack() if return_state else None
         return_reward = np.sign(reward) if self.clip_reward else reward
         truncated = np.zeros(self.num_envs, bool)
@@ -105,12 +153,6 @@ class AtariVecEnv(Env):
         self.training = False
         if hasattr(self.source, "training"):
             self.source.training = False
-
-    def render(self, mode="rgb_array", obs_size=None):
-        raise NotImplementedError("recording/rendering is outside the observation hot path (SURVEY.md §2 row 2)")
-
-    def close(self):
-        pass
 
 
 # ---- factories: atari_env.py:174-192, batched.  num_envs=1 + as_reference=True gives the single-env

@@ -383,6 +383,13 @@ int agym_plan_create(const agym_config *cfg, agym_plan **out_plan) {
         for (int m = 0; p5 && m < c.obs_h / 2; ++m)
             p5 = cy.s0[2 * m] == 5 * m && cy.s1[2 * m] == 5 * m + 1 && cy.s0[2 * m + 1] == 5 * m + 3 && cy.s1[2 * m + 1] == 5 * m + 4;
         d.tma_period5 = p5;
+        // k_ingest_gray_std: the standard ALE geometry, vertical weights (512, 1536) on even and (1536, 512) on odd rows
+        bool sg = p5 && fast_ingest && c.raw_c == 1 && c.raw_h == 210 && c.raw_w == 160 && c.obs_h == 84 && c.obs_w == 84;
+        for (int y = 0; sg && y < c.obs_h; ++y) {
+            const int b0 = cy.coef[y] & 0xffff, b1 = cy.coef[y] >> 16;
+            sg = (y & 1) ? (b0 == 1536 && b1 == 512) : (b0 == 512 && b1 == 1536);
+        }
+        d.std_gray = sg;
     }
     if (fast_ingest) {
         d.cx_pair = reinterpret_cast<const int4 *>(base + o_pair);
@@ -408,6 +415,7 @@ int agym_plan_create(const agym_config *cfg, agym_plan **out_plan) {
     pl->dev_packed.raw_h = static_cast<int32_t>(used.size());
     spans(ys0p, ys1p, pl->dev_packed.tma_span_rows);
     pl->dev_packed.tma_period5 = 0;   // packed rows are already gap-free
+    pl->dev_packed.std_gray = 0;
     *out_plan = pl;
     return AGYM_OK;
 }
@@ -496,13 +504,13 @@ int agym_observe_peripheral(const agym_plan *plan, const uint8_t *d_ring, const 
 
 int agym_observe_flexible(const agym_plan *plan, const uint8_t *d_ring, const int32_t *d_head, const double *d_action,
                           const int32_t *d_atype, const uint8_t *d_fov_ctrl, int32_t *d_loc, int32_t *d_res, int variant,
-                          int pad_h, int pad_w, uint8_t *d_out, void *stream) {
+                          int pad_h, int pad_w, uint8_t *d_out, int32_t *d_err, void *stream) {
     const int v = check_fov_args(plan, d_ring, d_head, d_action, d_fov_ctrl, d_loc, d_out);
     if (v != AGYM_OK) return v;
     if (!d_res || variant < AGYM_OUT_CROP || variant > AGYM_OUT_RESIZE_FULL) return AGYM_ERR_INVALID_ARG;
     if (variant == AGYM_OUT_CROP && (pad_h <= 0 || pad_w <= 0 || pad_w % 4 != 0)) return AGYM_ERR_INVALID_ARG;
     return ret(launch_observe_flexible(plan->dev, d_ring, d_head, d_action, d_atype, d_fov_ctrl, d_loc, d_res, variant,
-                                       pad_h, pad_w, d_out, as_stream(stream)));
+                                       pad_h, pad_w, d_out, d_err, as_stream(stream)));
 }
 
 int agym_table_cv2(int n_src, int n_dst, int zero_frac_at_border, int32_t *h_s0, int32_t *h_s1, int32_t *h_coef) {
@@ -536,6 +544,14 @@ int agym_table_blur(int r, int f, int32_t *h_xmin, float *h_w, uint16_t *h_q, si
     *taps = ax.taps;
     *halves = nh;
     return AGYM_OK;
+}
+
+int agym_record_step(int32_t n_envs, int is_reset, const double *d_raw_reward, const uint8_t *d_done,
+                     const uint8_t *d_reset_mask, int64_t *d_ep_len, double *d_cum_reward, const int32_t *d_loc,
+                     const int32_t *d_res, int32_t *d_trace_row, void *stream) {
+    if (n_envs < 0 || !d_ep_len || !d_cum_reward) return AGYM_ERR_INVALID_ARG;
+    return ret(launch_record_step(n_envs, is_reset, d_raw_reward, d_done, d_reset_mask, d_ep_len, d_cum_reward, d_loc, d_res,
+                                  d_trace_row, as_stream(stream)));
 }
 
 int agym_normalize(const uint8_t *d_src, size_t n_bytes, int dtype, void *d_dst, void *stream) {

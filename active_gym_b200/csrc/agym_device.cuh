@@ -60,6 +60,17 @@ __device__ __forceinline__ uint32_t quant_u8(float v) {
     return (uint32_t)min(max(q, 0), 255);
 }
 
+// FOV_RES action of the flexible fovea: fov_res = action (fov_env.py:323).  The reference fails for a window that is
+// not an integer size within the frame (float slice bounds; Resize of a window larger than the frame raises); a kernel
+// cannot raise, so it truncates, clamps to [1, S] and reports the event in the caller's error word (AGYM_ERR_RES_*).
+__device__ __forceinline__ void res_from_action(const DevPlan &p, double a0, double a1, int &rh, int &rw) {
+    const bool in_range = a0 >= 1.0 && a0 <= (double)p.S_h && a1 >= 1.0 && a1 <= (double)p.S_w;  // false for NaN
+    const bool integral = a0 == floor(a0) && a1 == floor(a1);
+    if (p.err && !(in_range && integral)) atomicOr(p.err, (in_range ? 0 : AGYM_ERR_RES_RANGE) | (integral ? 0 : AGYM_ERR_RES_FRACTION));
+    rh = min(max(in_range || a0 == a0 ? (int)fmin(fmax(a0, -1.0), 1.0e6) : 0, 1), p.S_h);
+    rw = min(max(in_range || a1 == a1 ? (int)fmin(fmax(a1, -1.0), 1.0e6) : 0, 1), p.S_w);
+}
+
 // fov_loc update of the fixed fovea (fov_env.py:187-199), split into the global loads and the
 // arithmetic so that a persistent kernel can issue the loads one env ahead.
 struct LocIn {

@@ -34,13 +34,10 @@ __global__ void __launch_bounds__(kThreads) k_observe_flexible(const __grid_cons
         if (mode == AGYM_FOV_RESET) {
             r = p.init_r; c = p.init_c; rh = p.f_h; rw = p.f_w;
         } else if (mode == AGYM_FOV_APPLY) {
-            const double a0 = action[2 * n], a1 = action[2 * n + 1];
+            const double a0 = action ? action[2 * n] : 0.0, a1 = action ? action[2 * n + 1] : 0.0;
             const int t = atype ? atype[n] : AGYM_ATYPE_FOV_LOC;
             if (t == AGYM_ATYPE_FOV_RES) {
-                // fov_res = action (fov_env.py:323); the reference raises for res > obs, the
-                // device clamps to [1, S] instead (the Python layer validates beforehand)
-                rh = min(max((int)a0, 1), p.S_h);
-                rw = min(max((int)a1, 1), p.S_w);
+                res_from_action(p, a0, a1, rh, rw);  // fov_res = action (fov_env.py:323)
                 r = clip_rint((double)r, 0.0, (double)(p.S_h - rh));
                 c = clip_rint((double)c, 0.0, (double)(p.S_w - rw));
             } else {
@@ -146,11 +143,10 @@ __global__ void __launch_bounds__(kThreads) k_observe_flexible_fast(const __grid
         if (mode == AGYM_FOV_RESET) {
             r = p.init_r; c = p.init_c; rh = p.f_h; rw = p.f_w;
         } else if (mode == AGYM_FOV_APPLY) {
-            const double a0 = action[2 * n], a1 = action[2 * n + 1];
+            const double a0 = action ? action[2 * n] : 0.0, a1 = action ? action[2 * n + 1] : 0.0;
             const int t = atype ? atype[n] : AGYM_ATYPE_FOV_LOC;
             if (t == AGYM_ATYPE_FOV_RES) {  // fov_res = action, then re-clamp loc (fov_env.py:322-324)
-                rh = min(max((int)a0, 1), p.S_h);
-                rw = min(max((int)a1, 1), p.S_w);
+                res_from_action(p, a0, a1, rh, rw);
                 r = clip_rint((double)r, 0.0, (double)(p.S_h - rh));
                 c = clip_rint((double)c, 0.0, (double)(p.S_w - rw));
             } else {
@@ -426,8 +422,7 @@ __global__ void __launch_bounds__(kFlexThreads + 32, 2) k_observe_flexible_v3(co
             r = p.init_r; c = p.init_c; rh = p.f_h; rw = p.f_w;
         } else if (q.mode == AGYM_FOV_APPLY) {
             if (q.t == AGYM_ATYPE_FOV_RES) {  // fov_res = action, then re-clamp loc (fov_env.py:322-324)
-                rh = min(max((int)q.a0, 1), p.S_h);
-                rw = min(max((int)q.a1, 1), p.S_w);
+                res_from_action(p, q.a0, q.a1, rh, rw);
                 r = clip_rint((double)r, 0.0, (double)(p.S_h - rh));
                 c = clip_rint((double)c, 0.0, (double)(p.S_w - rw));
             } else {
@@ -586,12 +581,6 @@ __global__ void __launch_bounds__(kFlexThreads + 32, 2) k_observe_flexible_v3(co
     cp_async_wait<0>();
     if (boss) {
         bulk_wait_read<0>();
-        // the last CTA to leave re-arms the counters for the next launch
-        __threadfence();
-        if (atomicAdd(counters + 1, 1) == (int)gridDim.x - 1) {
-            atomicExch(counters, 0);
-            atomicExch(counters + 1, 0);
-        }
     }
 }
 
@@ -601,8 +590,10 @@ __global__ void __launch_bounds__(kFlexThreads + 32, 2) k_observe_flexible_v3(co
 // --------------------------------------------------------------------------- launchers
 cudaError_t launch_observe_flexible(const DevPlan &p, const uint8_t *ring, const int32_t *head, const double *action,
                                     const int32_t *atype, const uint8_t *ctrl, int32_t *loc, int32_t *res, int variant,
-                                    int pad_h, int pad_w, uint8_t *out, cudaStream_t st) {
+                                    int pad_h, int pad_w, uint8_t *out, int32_t *err, cudaStream_t st) {
     cudaError_t e;
+    DevPlan q = p;
+    q.err = err;
     if (variant != AGYM_OUT_RESIZE_FULL && p.flexb && p.flexq && !g_disable_std && !g_flex_old) {
         // persistent kernel, 2 CTAs per SM: whatever the fixed buffers leave of ~113 KB goes to t1
         const int oh = variant == AGYM_OUT_CROP ? pad_h : p.S_h, ow = variant == AGYM_OUT_CROP ? pad_w : p.S_w;
@@ -620,12 +611,14 @@ cudaError_t launch_observe_flexible(const DevPlan &p, const uint8_t *ring, const
             cudaGetDevice(&dev);
             cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
             const int grid = std::min(p.N, 2 * sms);
+            // the env-claim counter starts every launch at zero (stream-ordered; a launch that faulted cannot leave it armed)
+            if ((e = cudaMemsetAsync(p.flex_counters, 0, 16, st)) != cudaSuccess) return e;
             if (variant == AGYM_OUT_CROP) {
                 if ((e = set_smem(k_observe_flexible_v3<AGYM_OUT_CROP>, fs)) != cudaSuccess) return e;
-                k_observe_flexible_v3<AGYM_OUT_CROP><<<grid, kFlexThreads + 32, fs, st>>>(p, ring, head, action, atype, ctrl, loc, res, oh, ow, (int)t1_cap, out, p.flex_counters);
+                k_observe_flexible_v3<AGYM_OUT_CROP><<<grid, kFlexThreads + 32, fs, st>>>(q, ring, head, action, atype, ctrl, loc, res, oh, ow, (int)t1_cap, out, p.flex_counters);
             } else {
                 if ((e = set_smem(k_observe_flexible_v3<AGYM_OUT_MASK>, fs)) != cudaSuccess) return e;
-                k_observe_flexible_v3<AGYM_OUT_MASK><<<grid, kFlexThreads + 32, fs, st>>>(p, ring, head, action, atype, ctrl, loc, res, oh, ow, (int)t1_cap, out, p.flex_counters);
+                k_observe_flexible_v3<AGYM_OUT_MASK><<<grid, kFlexThreads + 32, fs, st>>>(q, ring, head, action, atype, ctrl, loc, res, oh, ow, (int)t1_cap, out, p.flex_counters);
             }
             return cudaGetLastError();
         }
@@ -640,10 +633,10 @@ cudaError_t launch_observe_flexible(const DevPlan &p, const uint8_t *ring, const
         if (tile % 16 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 && fs <= 200 * 1024) {
             if (variant == AGYM_OUT_CROP) {
                 if ((e = set_smem(k_observe_flexible_fast<AGYM_OUT_CROP>, fs)) != cudaSuccess) return e;
-                k_observe_flexible_fast<AGYM_OUT_CROP><<<p.N, kThreads, fs, st>>>(p, ring, head, action, atype, ctrl, loc, res, oh, ow, t1_cap, out);
+                k_observe_flexible_fast<AGYM_OUT_CROP><<<p.N, kThreads, fs, st>>>(q, ring, head, action, atype, ctrl, loc, res, oh, ow, t1_cap, out);
             } else {
                 if ((e = set_smem(k_observe_flexible_fast<AGYM_OUT_MASK>, fs)) != cudaSuccess) return e;
-                k_observe_flexible_fast<AGYM_OUT_MASK><<<p.N, kThreads, fs, st>>>(p, ring, head, action, atype, ctrl, loc, res, oh, ow, t1_cap, out);
+                k_observe_flexible_fast<AGYM_OUT_MASK><<<p.N, kThreads, fs, st>>>(q, ring, head, action, atype, ctrl, loc, res, oh, ow, t1_cap, out);
             }
             return cudaGetLastError();
         }
@@ -651,7 +644,7 @@ cudaError_t launch_observe_flexible(const DevPlan &p, const uint8_t *ring, const
     const size_t smem = sizeof(float) * 2 * (size_t)p.plane;
 #define AGYM_LAUNCH_FLEX(V)                                                                              \
     if ((e = set_smem(k_observe_flexible<V>, smem)) != cudaSuccess) return e;                            \
-    k_observe_flexible<V><<<p.N, kThreads, smem, st>>>(p, ring, head, action, atype, ctrl, loc, res, pad_h, pad_w, out);
+    k_observe_flexible<V><<<p.N, kThreads, smem, st>>>(q, ring, head, action, atype, ctrl, loc, res, pad_h, pad_w, out);
     if (variant == AGYM_OUT_CROP) { AGYM_LAUNCH_FLEX(AGYM_OUT_CROP) }
     else if (variant == AGYM_OUT_MASK) { AGYM_LAUNCH_FLEX(AGYM_OUT_MASK) }
     else { AGYM_LAUNCH_FLEX(AGYM_OUT_RESIZE_FULL) }

@@ -738,6 +738,10 @@ cudaError_t launch_ingest_atari(const DevPlan &p, const uint8_t *fa, const uint8
     size_t smem = a16(sizeof(int32_t) * 3 * (p.S_w + p.S_h)) + a16(2 * (size_t)2 * p.S_h * p.raw_w);
     if (pcache) smem += a16(p.plane) + sizeof(float) * p.S_h * p.p_w;
     cudaError_t e;
+    if (p.std_gray && !g_disable_tma && !g_disable_tm && !g_units) {   // the standard ALE geometry has its own kernel
+        e = launch_ingest_gray_std(p, fa, fb, flags, ring, head, pcache, st);
+        if (e != cudaErrorNotSupported) return e;
+    }
     // units per env: index into the plan's span table (gray: 3 units of 28 rows; RGB: 7 units of 12 rows = two rows
     // for each of the 6 row segments of the consumer warps, and three CTAs still fit an SM)
     // With the gap-free stages of the tensor-copy path two units of 42 rows fit three CTAs per SM for gray frames

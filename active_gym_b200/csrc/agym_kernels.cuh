@@ -45,6 +45,7 @@ struct DevPlan {
     // {next env, CTAs done}: work counter of the persistent flexible kernel; zero between launches (the last CTA
     // re-arms it), so a plan must not run agym_observe_flexible on two streams at once
     int32_t *flex_counters;
+    int32_t *err;           // per-launch: the caller's device error word (AGYM_ERR_RES_* bits) or null
     const int32_t *pool_i;  // pool base viewed as int32
     int32_t S_max;
     // ---- fast paths (0 = geometry not eligible, use the generic kernels)
@@ -53,6 +54,7 @@ struct DevPlan {
     int32_t fast_ingest;
     int32_t tma_span_rows[8];  // TMA ingest: largest source-row span of a unit when an env is cut into 1..8 units (0 = n/a)
     int32_t tma_period5;       // vertical scale 2.5: output row 2m samples raw rows {5m, 5m+1}, row 2m+1 {5m+3, 5m+4}
+    int32_t std_gray;          // gray 210x160 -> 84x84 with the period-5 rows and (512,1536)/(1536,512) vertical weights: k_ingest_gray_std
     int32_t fast_ingest_rgb;   // 3-channel frames: every column pair's four source pixels lie among s0 .. s0 + 3
     const int4 *cx_pair;    // [S_w / 2]
     const int2 *cy_bs;      // [S_h]
@@ -82,6 +84,9 @@ struct ExpandStd {
 
 cudaError_t launch_ingest_atari(const DevPlan &p, const uint8_t *fa, const uint8_t *fb, const uint8_t *flags,
                                 uint8_t *ring, int32_t *head, float *pcache, cudaStream_t st);
+// standard-geometry gray ingest (agym_ingest_std.cu); cudaErrorNotSupported = not eligible, use launch_ingest_atari's kernels
+cudaError_t launch_ingest_gray_std(const DevPlan &p, const uint8_t *fa, const uint8_t *fb, const uint8_t *flags,
+                                   uint8_t *ring, int32_t *head, float *pcache, cudaStream_t st);
 cudaError_t launch_ingest_dmc(const DevPlan &p, const uint8_t *f, const uint8_t *flags, uint8_t *ring,
                               int32_t *head, float *pcache, cudaStream_t st);
 cudaError_t launch_stack(const DevPlan &p, const uint8_t *ring, const int32_t *head, uint8_t *out, cudaStream_t st);
@@ -92,8 +97,11 @@ cudaError_t launch_observe_peripheral(const DevPlan &p, const ExpandStd *ew, con
                                       uint8_t *out, cudaStream_t st);
 cudaError_t launch_observe_flexible(const DevPlan &p, const uint8_t *ring, const int32_t *head, const double *action,
                                     const int32_t *atype, const uint8_t *ctrl, int32_t *loc, int32_t *res, int variant,
-                                    int pad_h, int pad_w, uint8_t *out, cudaStream_t st);
+                                    int pad_h, int pad_w, uint8_t *out, int32_t *err, cudaStream_t st);
 cudaError_t launch_normalize(const uint8_t *src, size_t n, int dtype, void *dst, cudaStream_t st);
 cudaError_t launch_synth(uint8_t *dst, size_t n, uint64_t seed, cudaStream_t st);
+cudaError_t launch_record_step(int n, int is_reset, const double *raw_reward, const uint8_t *done, const uint8_t *reset_mask,
+                               int64_t *ep_len, double *cum_reward, const int32_t *loc, const int32_t *res,
+                               int32_t *trace_row, cudaStream_t st);
 
 }  // namespace agym

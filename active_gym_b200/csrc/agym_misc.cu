@@ -42,6 +42,39 @@ __global__ void k_normalize(const uint4 *__restrict__ src, void *__restrict__ ds
     }
 }
 
+// ----------------------------------------------------------------------------- record
+// RecordWrapper's episode counters (fov_env.py:15-67: reset zeroes cumulative_reward / ep_len, step adds one
+// step and info["raw_reward"]) and the fov_loc / fov_res trace of save_transition (fov_env.py:152-154, 160-163,
+// 205-207, 216-219, 253-256, 262-265, 332-335, 351-354: appended on reset and on every step that is not done),
+// for N envs at once.  One thread per env.
+__global__ void k_record_step(int n, int is_reset, const double *__restrict__ raw_reward, const uint8_t *__restrict__ done,
+                              const uint8_t *__restrict__ reset_mask, long long *__restrict__ ep_len,
+                              double *__restrict__ cum_reward, const int32_t *__restrict__ loc,
+                              const int32_t *__restrict__ res, int32_t *__restrict__ trace_row) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    long long len = ep_len[i];
+    double cum = cum_reward[i];
+    int valid;
+    if (is_reset) {
+        const bool mine = !reset_mask || reset_mask[i];
+        if (mine) { len = 0; cum = 0.0; }
+        valid = mine ? 1 : 0;
+    } else {
+        len += 1;
+        cum += raw_reward ? raw_reward[i] : 0.0;
+        valid = (done && done[i]) ? 0 : 1;
+    }
+    ep_len[i] = len;
+    cum_reward[i] = cum;
+    if (trace_row) {
+        int32_t *t = trace_row + (size_t)i * 6;
+        t[0] = loc ? loc[2 * i] : 0; t[1] = loc ? loc[2 * i + 1] : 0;
+        t[2] = res ? res[2 * i] : 0; t[3] = res ? res[2 * i + 1] : 0;
+        t[4] = (int32_t)len; t[5] = valid;
+    }
+}
+
 // ------------------------------------------------------------------------------ synth
 __global__ void k_synth(uint4 *dst, size_t n_vec, uint64_t seed) {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n_vec; i += (size_t)gridDim.x * blockDim.x) {
@@ -72,6 +105,15 @@ cudaError_t launch_normalize(const uint8_t *src, size_t n, int dtype, void *dst,
     if (dtype == 0) k_normalize<0><<<blocks, 256, 0, st>>>(s4, dst, n_vec);
     else if (dtype == 1) k_normalize<1><<<blocks, 256, 0, st>>>(s4, dst, n_vec);
     else k_normalize<2><<<blocks, 256, 0, st>>>(s4, dst, n_vec);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_record_step(int n, int is_reset, const double *raw_reward, const uint8_t *done, const uint8_t *reset_mask,
+                               int64_t *ep_len, double *cum_reward, const int32_t *loc, const int32_t *res,
+                               int32_t *trace_row, cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    k_record_step<<<(n + 255) / 256, 256, 0, st>>>(n, is_reset, raw_reward, done, reset_mask,
+                                                   reinterpret_cast<long long *>(ep_len), cum_reward, loc, res, trace_row);
     return cudaGetLastError();
 }
 

@@ -11,9 +11,9 @@ from typing import Optional, Tuple
 
 import numpy as np
 
-from .atari_env import _path_from_args
+from .atari_env import _VecBase
 from .engine import LUMA_DMC
-from .spaces import Box, Env
+from .spaces import Box
 
 
 class DMCEnvArgs:
@@ -41,29 +41,19 @@ class DMCEnvArgs:
             self.__setattr__(k, v)
 
 
-class DMCVecEnv(Env):
+class DMCVecEnv(_VecBase):
     """N DMC environments; observation = (N, K, S_h, S_w) uint8 CUDA tensor (dmc_env.py:78-253)."""
 
     def __init__(self, args, num_envs: int = 1, source=None, device=None):
         if not args.from_pixels or not args.grey:
             raise NotImplementedError("only the from_pixels=True, grey=True branch is on the observation hot path")
-        self.args = args
-        self.num_envs = int(num_envs)
-        self.obs_size = tuple(args.obs_size)
-        self.frame_stack = args.frame_stack
-        self.action_repeat = args.action_repeat
-        self.clip_reward = args.clip_reward
         if source is None:
             from .sources import DMCPool
-            source = DMCPool(args, self.num_envs, workers=getattr(args, "sim_workers", 1))
-        self.source = source
+            source = DMCPool(args, int(num_envs), workers=getattr(args, "sim_workers", 1))
         # dmc_env.py:182 applies COLOR_BGR2GRAY to an RGB render: channel 0 gets the blue weight
-        self.path = _path_from_args(args, self.num_envs, tuple(source.raw_shape), LUMA_DMC,
-                                    device or getattr(args, "device", None))
-        self.device = self.path.device
+        self._init_engine(args, num_envs, source, LUMA_DMC, device)
         self._true_low, self._true_high = source.true_low, source.true_high
         self.action_space = Box(low=-1.0, high=1.0, shape=self._true_low.shape, dtype=np.float32)  # dmc_env.py:110-115
-        self.observation_space = Box(low=-1., high=1., shape=(self.frame_stack,) + self.obs_size, dtype=np.float32)
 
     @property
     def reward_range(self):
@@ -78,15 +68,23 @@ class DMCVecEnv(Env):
         """dmc_env.py:197-209."""
         frames, flags = self.source.reset(mask)
         self.path.ingest_dmc(frames, flags)
+        self._frames_enqueued()
         state = self.path.stack() if return_state else None
         return state, self._info(np.zeros(self.num_envs))
 
-    def step(self, action, return_state=True):
-        """dmc_env.py:211-234."""
+    def step_async(self, action):
+        """dmc_env.py:211-226: steps the simulators (host) and enqueues copy + ingest; returns at once."""
         action = np.asarray(action, np.float32).reshape(self.num_envs, -1)
         assert (action >= -1.0).all() and (action <= 1.0).all()  # dmc_env.py:212
         frames, flags, reward, done = self.source.step(action)
         self.path.ingest_dmc(frames, flags)
+        self._frames_enqueued()
+        self._pending = (reward, done)
+
+    def step_wait(self, return_state=True):
+        """dmc_env.py:227-234."""
+        reward, done = self._pending
+        self._pending = None
         state = self.path.stack() if return_state else None
         return_reward = np.sign(reward) if self.clip_reward else reward
         return state, return_reward, done, np.zeros(self.num_envs, bool), self._info(reward)
@@ -95,9 +93,6 @@ class DMCVecEnv(Env):
         pass
 
     def eval(self):
-        pass
-
-    def close(self):
         pass
 
 

@@ -39,7 +39,7 @@ class ObservationPath:
                  luma: Sequence[int] = LUMA_RGB, fov_size: Optional[Tuple[int, int]] = None,
                  fov_init_loc: Sequence[float] = (0, 0), sensory_action_mode: str = "absolute",
                  sensory_action_space: Sequence[float] = (0.0, 0.0), peripheral_res: Optional[Tuple[int, int]] = None,
-                 device: Optional[torch.device] = None, cache_peripheral: bool = True):
+                 device: Optional[torch.device] = None, cache_peripheral: bool = True, buffers: Optional[dict] = None):
         if not torch.cuda.is_available():
             raise RuntimeError("active_gym_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
@@ -71,15 +71,27 @@ class ObservationPath:
             _lib.check(self._L.agym_plan_create(C.byref(cfg), C.byref(self._plan)), "agym_plan_create")
         N, K, (S_h, S_w) = self.n_envs, self.frame_stack, self.obs_size
         dev = self.device
-        self.ring = torch.zeros((N, K, S_h, S_w), dtype=torch.uint8, device=dev)
-        self.head = torch.full((N,), K - 1, dtype=torch.int32, device=dev)
-        self.loc = torch.zeros((N, 2), dtype=torch.int32, device=dev)
-        self.res = torch.zeros((N, 2), dtype=torch.int32, device=dev)
-        if self.fov_size:
-            self.res[:, 0], self.res[:, 1] = self.fov_size
-        self.pcache = None
-        if self.peripheral_res and cache_peripheral:
-            self.pcache = torch.zeros((N, K) + self.peripheral_res, dtype=torch.float32, device=dev)
+        if buffers is not None:
+            # slices of a larger batch owned by the caller (PipelinedPath): contiguous, already initialised
+            self.ring, self.head, self.loc, self.res = buffers["ring"], buffers["head"], buffers["loc"], buffers["res"]
+            self.pcache, self.err = buffers.get("pcache"), buffers.get("err")
+            for t, shape in ((self.ring, (N, K, S_h, S_w)), (self.head, (N,)), (self.loc, (N, 2)), (self.res, (N, 2))):
+                if tuple(t.shape) != shape or not t.is_contiguous() or t.device != dev:
+                    raise ValueError("buffers must be contiguous device tensors of this path's shapes")
+            if self.err is None:
+                self.err = torch.zeros((1,), dtype=torch.int32, device=dev)
+        else:
+            self.ring = torch.zeros((N, K, S_h, S_w), dtype=torch.uint8, device=dev)
+            self.head = torch.full((N,), K - 1, dtype=torch.int32, device=dev)
+            self.loc = torch.zeros((N, 2), dtype=torch.int32, device=dev)
+            self.res = torch.zeros((N, 2), dtype=torch.int32, device=dev)
+            if self.fov_size:
+                self.res[:, 0], self.res[:, 1] = self.fov_size
+            self.pcache = None
+            if self.peripheral_res and cache_peripheral:
+                self.pcache = torch.zeros((N, K) + self.peripheral_res, dtype=torch.float32, device=dev)
+            # device error word of the flexible fovea (AGYM_ERR_RES_*): see read_errors()
+            self.err = torch.zeros((1,), dtype=torch.int32, device=dev)
         self._ctrl_reset = torch.full((N,), _lib.FOV_RESET, dtype=torch.uint8, device=dev)
 
     def __del__(self):
@@ -232,9 +244,27 @@ class ObservationPath:
         with torch.cuda.device(self.device):
             _lib.check(self._L.agym_observe_flexible(self._plan, _ptr(self.ring), _ptr(self.head), _ptr(act), _ptr(at),
                                                      _ptr(ctrl_t), _ptr(self.loc), _ptr(self.res), VARIANTS[variant],
-                                                     int(pad[0]), int(pad[1]), _ptr(out), self._stream()),
+                                                     int(pad[0]), int(pad[1]), _ptr(out), _ptr(self.err), self._stream()),
                        "agym_observe_flexible")
         return out
+
+    def read_errors(self) -> int:
+        """Device error word (``_lib.ERR_RES_*`` bits: FOV_RES actions the reference would have failed on were
+        clamped / truncated by a kernel).  Reading it synchronises with the device; it is cleared when non-zero."""
+        v = int(self.err.item())
+        if v:
+            self.err.zero_()
+        return v
+
+    def record_step(self, ep_len: torch.Tensor, cum_reward: torch.Tensor, raw_reward=None, done=None, reset_mask=None,
+                    is_reset: bool = False, trace_row: Optional[torch.Tensor] = None, with_res: bool = False) -> None:
+        """RecordWrapper's counters and fov trace (fov_env.py:15-67, 152-154, 205-207) on the device: see
+        ``agym_record_step``.  ``ep_len`` int64 (N,), ``cum_reward`` float64 (N,), updated in place."""
+        with torch.cuda.device(self.device):
+            _lib.check(self._L.agym_record_step(self.n_envs, int(is_reset), _ptr(raw_reward), _ptr(done), _ptr(reset_mask),
+                                                _ptr(ep_len), _ptr(cum_reward), _ptr(self.loc),
+                                                _ptr(self.res) if with_res else None, _ptr(trace_row), self._stream()),
+                       "agym_record_step")
 
     _NORM_DTYPES = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2}
 

@@ -18,37 +18,140 @@ from .spaces import Box, Dict, Discrete, Wrapper
 
 
 class RecordWrapper(Wrapper):
-    """Episode counters of fov_env.py:15-67, batched: ``info["reward"]`` is the cumulative raw
-    reward and ``info["ep_len"]`` the step count of every env.  Trajectory recording to
-    mp4/.pt (fov_env.py:70-102) is a debugging aid outside the hot path and is not provided."""
+    """fov_env.py:15-105 for N envs, on the device: ``ep_len`` / ``cumulative_reward`` are (N,) CUDA tensors
+    updated by ``agym_record_step`` (one launch per step, issued after the fovea update so that the same launch
+    appends ``fov_loc`` / ``fov_res`` to the trace); ``info["reward"]`` is the cumulative raw reward and
+    ``info["ep_len"]`` the step count of every env.
+
+    ``record=True`` keeps, like the reference's ``record_buffer``, the per-step ``fov_loc`` (``fov_res``) of every
+    env that is not done — in a device trace ring of ``args.record_capacity`` calls (default 4096) — and the actions /
+    rewards / done flags of the same calls on the host; ``save_record_to_file`` writes one env's last completed
+    episode as the reference's ``.pt`` dictionary (fov_env.py:90-102).  The mp4 of rendered frames is not written
+    (no renderer on this path): ``"rgb"`` is ``None``."""
 
     def __init__(self, env, args):
         super().__init__(env)
         self.args = args
         self.record = bool(args.record)
+        base = env.unwrapped
+        self._path = base.path
+        self.num_envs = base.num_envs
+        self.host_obs = bool(getattr(base, "host_obs", False))
+        self.record_capacity = int(getattr(args, "record_capacity", 4096))
+        self.trace = None
+        self._calls = 0        # record calls so far (reset or step); call c lives in trace row c % capacity
+        self._host_log = None
         if self.record:
-            raise NotImplementedError("record=True (mp4/.pt trajectory dumps, fov_env.py:70-102) is out of scope")
-        n = env.num_envs
-        self.cumulative_reward = np.zeros(n, np.float64)
-        self.ep_len = np.zeros(n, np.int64)
+            import collections
+            self.trace = torch.zeros((self.record_capacity, self.num_envs, 6), dtype=torch.int32, device=self._path.device)
+            self._host_log = collections.deque(maxlen=self.record_capacity)
+        self._deferred = None
+        self._with_res = False
+        self._counters_host = None
+
+    # ---- state the reference exposes as attributes
+    @property
+    def ep_len(self) -> torch.Tensor:
+        return self._path.ep_len
+
+    @property
+    def cumulative_reward(self) -> torch.Tensor:
+        return self._path.cum_reward
+
+    def _commit(self, with_res: bool = False):
+        """Issues the deferred counter / trace update (after the wrapper above has moved the fovea, if there is one)."""
+        kw, log = self._deferred
+        self._deferred = None
+        row = None
+        if self.record:
+            row = self.trace[self._calls % self.record_capacity]
+            self._host_log.append(log)
+            self._calls += 1
+        self._counters_host = self._path.record_step(trace_row=row, with_res=with_res, host_out=self.host_obs, **kw)
 
     def _add_info(self, info):
-        info["reward"] = self.cumulative_reward.copy()
-        info["ep_len"] = self.ep_len.copy()
+        if self.host_obs:   # pinned host copies, valid once the step has been waited for
+            info["ep_len"], info["reward"] = self._counters_host[0].numpy(), self._counters_host[1].numpy()
+        else:
+            info["reward"] = self._path.cum_reward.clone()
+            info["ep_len"] = self._path.ep_len.clone()
         return info
 
-    def reset(self, seed=None, options=None, mask=None, return_state=True):
+    def reset(self, seed=None, options=None, mask=None, return_state=True, defer_record=False):
         state, info = self.env.reset(seed, options, mask=mask, return_state=return_state)
-        sel = slice(None) if mask is None else np.asarray(mask, bool)
-        self.cumulative_reward[sel] = 0
-        self.ep_len[sel] = 0
-        return state, self._add_info(info)
+        self._deferred = (dict(reset_mask=mask, is_reset=True), dict(reset=True, mask=None if mask is None else np.array(mask, bool)))
+        if not defer_record:
+            self._commit()
+            info = self._add_info(info)
+        return state, info
+
+    def step_async(self, action):
+        self.env.step_async(action)
+        self._action = action
+
+    def step_wait(self, return_state=True, defer_record=False, full_action=None):
+        state, return_reward, done, truncated, info = self.env.step_wait(return_state=return_state)
+        raw = info.get("raw_reward", return_reward)
+        log = None
+        if self.record:
+            log = dict(action=full_action if full_action is not None else self._action, return_reward=np.array(return_reward),
+                       raw_reward=np.array(raw), done=np.array(done, bool))
+        self._deferred = (dict(raw_reward=raw, done=done, is_reset=False), log)
+        if not defer_record:
+            self._commit()
+            info = self._add_info(info)
+        return state, return_reward, done, truncated, info
 
     def step(self, action, return_state=True):
-        state, return_reward, done, truncated, info = self.env.step(action, return_state=return_state)
-        self.ep_len += 1
-        self.cumulative_reward += np.asarray(info.get("raw_reward", return_reward), np.float64)
-        return state, return_reward, done, truncated, self._add_info(info)
+        self.step_async(action)
+        return self.step_wait(return_state=return_state)
+
+    def episode_record(self, env_index: int = 0) -> dict:
+        """The last COMPLETED episode of one env (what the reference keeps in ``prev_record_buffer`` after the reset
+        that follows it), in the reference's record layout."""
+        if not self.record:
+            raise RuntimeError("record=False: nothing was recorded")
+        n_calls = min(self._calls, self.record_capacity)
+        first = self._calls - n_calls
+        order = [(c % self.record_capacity) for c in range(first, self._calls)]
+        self._path.sync()
+        tr = self.trace[order, env_index].cpu().numpy()        # (calls, 6) in call order
+        logs = list(self._host_log)
+        resets = [i for i, lg in enumerate(logs) if lg.get("reset") and (lg["mask"] is None or lg["mask"][env_index])]
+        if len(resets) < 2:
+            raise RuntimeError("no completed episode in the trace yet (the reference keeps it only after the next reset)")
+        i0, i1 = resets[-2], resets[-1]
+        rec = {"rgb": None, "state": [], "action": [], "reward": [], "done": [], "truncated": [], "info": [],
+               "return_reward": [], "fov_loc": [], "fov_size": tuple(getattr(self.args, "fov_size", ()) or ())}
+        if self._with_res:
+            rec["fov_res"] = []
+        cum, n_states = 0.0, 0
+        for i in range(i0, i1):
+            lg, t = logs[i], tr[i]
+            if t[5]:   # reset entry, or a step that was not done (fov_env.py:72-75, 216-219)
+                n_states += 1
+                rec["fov_loc"].append(t[0:2].copy())
+                if self._with_res:
+                    rec["fov_res"].append(t[2:4].copy())
+            if lg.get("reset"):
+                continue
+            a = lg["action"]
+            rec["action"].append({k: np.asarray(v.cpu() if isinstance(v, torch.Tensor) else v)[env_index] for k, v in a.items()}
+                                 if isinstance(a, dict) else np.asarray(a)[env_index])
+            cum += float(np.asarray(lg["raw_reward"])[env_index])
+            rec["reward"].append(cum)          # the reference logs the cumulative raw reward (fov_env.py:62-66)
+            rec["return_reward"].append(float(np.asarray(lg["return_reward"])[env_index]))
+            if n_states > 1:   # fov_env.py:80-85: done / info are kept only once a second state exists
+                rec["done"].append(bool(lg["done"][env_index]))
+                rec["info"].append({"ep_len": int(t[4]), "fov_loc": t[0:2].copy()})
+            rec["truncated"].append(False)
+        rec["state"] = [0] * len(rec["reward"])   # fov_env.py:99
+        return rec
+
+    def save_record_to_file(self, file_path: str, env_index: int = 0):
+        """fov_env.py:90-102 without the video: ``torch.save`` of the episode dictionary."""
+        if self.record:
+            torch.save(self.episode_record(env_index), file_path)
 
 
 class FixedFovealEnv(Wrapper):
@@ -74,6 +177,7 @@ class FixedFovealEnv(Wrapper):
         base = self.env.unwrapped
         self.path = base.path
         self.num_envs = base.num_envs
+        self.host_obs = bool(getattr(base, "host_obs", False))
         if self.path.fov_size != self.fov_size:
             raise ValueError("the base env was built from different args (fov_size mismatch)")
         # fov_env.py:125-129 declares Box(low=sas[0], high=sas[1], dtype=int): shape (1,) and, in
@@ -84,6 +188,9 @@ class FixedFovealEnv(Wrapper):
         })
         shape = self.obs_size if (self.mask_out or self.resize) else self.fov_size
         self.observation_space = Box(low=-1., high=1., shape=(self.env.frame_stack,) + tuple(shape), dtype=np.float32)
+        self._rec = self.env if isinstance(self.env, RecordWrapper) else None
+        self._obs = None
+        self._host = None
 
     # ---- state the reference exposes as attributes
     @property
@@ -95,10 +202,24 @@ class FixedFovealEnv(Wrapper):
         return "mask" if self.mask_out else ("resize_full" if self.resize else "crop")
 
     def _observe(self, action, ctrl, action_type=None):
-        return self.path.observe_fixed(action, variant=self.variant, ctrl=ctrl)
+        return self.path.observe_fixed(action, variant=self.variant, ctrl=ctrl, host_out=self.host_obs)
+
+    def _run_observe(self, action, ctrl, action_type=None):
+        r = self._observe(action, ctrl, action_type)
+        if self.host_obs:
+            self._obs, self._host = r
+        else:
+            self._obs, self._host = r, None
+
+    def _result_obs(self):
+        """Device tensor, or (host_obs) the pinned host tensor once the shard streams have finished."""
+        if self.host_obs:
+            self.path.sync()
+            return self._host[0]
+        return self._obs
 
     def _fov_info(self, info):
-        info["fov_loc"] = self.path.loc.clone()
+        info["fov_loc"] = self._host[1].numpy() if self.host_obs else self.path.loc.clone()
         return info
 
     @staticmethod
@@ -107,17 +228,48 @@ class FixedFovealEnv(Wrapper):
             return "reset"
         return np.where(np.asarray(mask, bool), _lib.FOV_RESET, _lib.FOV_KEEP).astype(np.uint8)
 
+    _with_res = False
+
     def reset(self, mask=None):
         """fov_env.py:156-164 (takes no seed/options, like the reference)."""
-        _, info = self.env.reset(mask=mask, return_state=False)
-        obs = self._observe(None, self._ctrl_for_reset(mask, self.num_envs))
+        rec = self._rec
+        _, info = self.env.reset(mask=mask, return_state=False, **({"defer_record": True} if rec is not None else {}))
+        self._run_observe(None, self._ctrl_for_reset(mask, self.num_envs))
+        if rec is not None:
+            rec._with_res = self._with_res
+            rec._commit(with_res=self._with_res)
+        obs = self._result_obs()
+        if rec is not None:
+            info = rec._add_info(info)
         return obs, self._fov_info(info)
+
+    def step_async(self, action):
+        """Steps the simulators, then enqueues copy + ingest + fovea update + observation; returns at once."""
+        self.env.step_async(action["motor_action"])
+        self._action = action
+        self._run_observe(action["sensory_action"], None, action.get("sensory_action_type"))
+
+    def step_wait(self):
+        """fov_env.py:209-221: collects (obs, reward, done, truncated, info) of the step submitted last."""
+        rec = self._rec
+        kw = dict(defer_record=True, full_action=self._action) if rec is not None else {}
+        _, reward, done, truncated, info = self.env.step_wait(return_state=False, **kw)
+        if rec is not None:
+            rec._with_res = self._with_res
+            rec._commit(with_res=self._with_res)
+        obs = self._result_obs()
+        if rec is not None:
+            info = rec._add_info(info)
+        self._raise_device_errors()
+        return obs, reward, done, truncated, self._fov_info(info)
 
     def step(self, action):
         """fov_env.py:209-221.  action = {"motor_action": (N,), "sensory_action": (N,2)}."""
-        _, reward, done, truncated, info = self.env.step(action["motor_action"], return_state=False)
-        obs = self._observe(action["sensory_action"], None, action.get("sensory_action_type"))
-        return obs, reward, done, truncated, self._fov_info(info)
+        self.step_async(action)
+        return self.step_wait()
+
+    def _raise_device_errors(self):
+        pass
 
 
 class FlexibleFovealEnvActionType(IntEnum):  # fov_env.py:236-238
@@ -158,11 +310,29 @@ class FlexibleFovealEnv(FixedFovealEnv):
 
     def _observe(self, action, ctrl, action_type=None):
         self._check_res(action, action_type)
-        return self.path.observe_flexible(action, action_type, variant=self.variant, ctrl=ctrl)
+        self._device_actions = isinstance(action, torch.Tensor) and action.device.type == "cuda"
+        return self.path.observe_flexible(action, action_type, variant=self.variant, ctrl=ctrl, host_out=self.host_obs)
+
+    def _raise_device_errors(self):
+        """FOV_RES actions given as device tensors cannot be validated before the launch; the kernels report what they
+        had to clamp / truncate in a device error word.  It is polled without stalling the device pipeline (an
+        asynchronous 4-byte copy per step, looked at one step later), so the error surfaces at the latest on the
+        step after the offending one."""
+        if self.validate_actions and getattr(self, "_device_actions", False):
+            bits = self.path.read_errors() if self.host_obs else self.path.poll_errors()
+            if bits:
+                what = [m for b, m in ((_lib.ERR_RES_RANGE, "outside [1, obs_size]"), (_lib.ERR_RES_FRACTION, "not integral")) if bits & b]
+                raise ValueError("FOV_RES actions must be integer window sizes within [1, obs_size] (fov_env.py:322-324 would fail): "
+                                 + ", ".join(what) + "; the affected windows were clamped")
+
+    _with_res = True
 
     def _fov_info(self, info):
-        info["fov_loc"] = self.path.loc.clone()
-        info["fov_res"] = self.path.res.clone()
+        if self.host_obs:
+            info["fov_loc"], info["fov_res"] = self._host[1].numpy(), self._host[2].numpy()
+        else:
+            info["fov_loc"] = self.path.loc.clone()
+            info["fov_res"] = self.path.res.clone()
         return info
 
 
@@ -182,7 +352,7 @@ class FixedFovealPeripheralEnv(FixedFovealEnv):
             raise ValueError("the base env was built from different args (peripheral_res mismatch)")
 
     def _observe(self, action, ctrl, action_type=None):
-        return self.path.observe_peripheral(action, ctrl=ctrl)
+        return self.path.observe_peripheral(action, ctrl=ctrl, host_out=self.host_obs)
 
 
 class SingleEnvAdapter:

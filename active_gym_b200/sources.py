@@ -10,6 +10,16 @@ the simulator-side scalars (reward, done).
                      episodic-life termination (atari_env.py:84-108, 123-131, 135-140).
 * ``DMCPool``      — N ``dm_control`` tasks (dmc_env.py:100-106, 166-173, 202-224).
 * ``SyntheticAtariSource`` / ``SyntheticDMCSource`` — device-generated frames for benchmarks.
+* ``PinnedFrameSource`` — pre-generated frames in pinned HOST memory, cycled: the stand-in for a simulator pool
+                     whose stepping cost is not what is being measured (end-to-end benchmark, pipeline tests).
+
+Staging protocol (host sources): a source owns TWO sets of pinned staging buffers and alternates between them on
+every ``reset`` / ``step`` call, and the env calls ``source.frames_consumed(events)`` with CUDA events recorded
+(one per copy stream) after the asynchronous host->device copies of a call were enqueued; before a set is written
+again the source waits for the events of the call that last used it.  So an in-flight copy is never overwritten.
+Row packing: ``set_used_rows(rows)`` (called by the env with ``ObservationPath.used_rows``) makes an Atari source
+write only the raw rows the resize samples — (N, 168, 160) instead of (N, 210, 160) — so that the copy is one
+contiguous block per shard; ``packed_rows`` tells the env which layout it gets.
 """
 from __future__ import annotations
 
@@ -62,7 +72,27 @@ def _pinned(shape, dtype=torch.uint8) -> torch.Tensor:
     return t
 
 
-class ALEPool:
+class _Staging:
+    """Two alternating sets of pinned buffers + the events that guard them (see the module docstring)."""
+
+    def _init_staging(self, make_set):
+        self._sets = [make_set(), make_set()]
+        self._events = [None, None]
+        self._cur = 0
+
+    def _next_set(self):
+        self._cur ^= 1
+        for ev in self._events[self._cur] or ():
+            ev.synchronize()
+        self._events[self._cur] = None
+        return self._sets[self._cur]
+
+    def frames_consumed(self, events) -> None:
+        """The env recorded `events` (one per copy stream) after enqueueing the copies that read the set handed out last."""
+        self._events[self._cur] = list(events)
+
+
+class ALEPool(_Staging):
     """Host pool of Arcade Learning Environment instances (the L0 simulators of SURVEY.md §1)."""
 
     raw_shape = (210, 160, 1)
@@ -90,19 +120,36 @@ class ALEPool:
         self.n_actions = len(actions)
         self.lives = [0] * self.num_envs
         self.life_termination = [False] * self.num_envs
+        self.packed_rows = False
+        self._rows = None
+        self._alloc(210)
+        self.flags = np.zeros(self.num_envs, np.uint8)
+
+    def _alloc(self, rows: int):
         n = self.num_envs
-        self.frames_a, self.frames_b = _pinned((n, 210, 160)), _pinned((n, 210, 160))
+        self._init_staging(lambda: (_pinned((n, rows, 160)), _pinned((n, rows, 160))))
+        self.frames_a, self.frames_b = self._sets[0]
         self._fa, self._fb = self.frames_a.numpy(), self.frames_b.numpy()
-        self.flags = np.zeros(n, np.uint8)
+
+    def set_used_rows(self, rows) -> None:
+        """Write only these raw rows (ascending) of every screen: the rows cv2's resize samples (atari_env.py:74)."""
+        self._rows = np.asarray(rows, np.int64)
+        self.packed_rows = True
+        self._alloc(len(self._rows))
+
+    def _flip(self):
+        self.frames_a, self.frames_b = self._next_set()
+        self._fa, self._fb = self.frames_a.numpy(), self.frames_b.numpy()
 
     def _screen(self, ale, dst):
-        g = ale.getScreenGrayscale()
-        dst[...] = np.asarray(g).reshape(210, 160)
+        g = np.asarray(ale.getScreenGrayscale()).reshape(210, 160)
+        dst[...] = g if self._rows is None else g[self._rows]
 
     def reset(self, mask: Optional[np.ndarray] = None):
         """atari_env.py:84-113 minus the buffer work.  Returns (frames, frames, flags)."""
         # the reference draws its no-op count from the global `random` (atari_env.py:96); draw them here,
         # serially and in env order, so that worker threads do not change the stream
+        self._flip()
         noops = [None] * self.num_envs
         for i in range(self.num_envs):
             if (mask is None or mask[i]) and not self.life_termination[i]:
@@ -139,6 +186,7 @@ class ALEPool:
     def step(self, motor_action: Sequence[int]):
         """atari_env.py:119-140 minus the buffer work.  Returns (fa, fb, flags, reward, done)."""
         n = self.num_envs
+        self._flip()
         reward, done = np.zeros(n, np.float64), np.zeros(n, bool)
         motor_action = np.asarray(motor_action).reshape(n)
 
@@ -168,7 +216,7 @@ class ALEPool:
         self._workers.close()
 
 
-class DMCPool:
+class DMCPool(_Staging):
     """Host pool of dm_control tasks; renders at obs_size (dmc_env.py:175-180)."""
 
     def __init__(self, args, num_envs: int, env_factory: Optional[Callable[[int], object]] = None, workers: int = 1):
@@ -188,7 +236,8 @@ class DMCPool:
         self.true_high = np.asarray(spec.maximum, np.float32) + np.zeros(spec.shape, np.float32)
         h, w = self.obs_size
         self.raw_shape = (h, w, 3)
-        self.frames = _pinned((self.num_envs, h, w, 3))
+        self._init_staging(lambda: _pinned((self.num_envs, h, w, 3)))
+        self.frames = self._sets[0]
         self._f = self.frames.numpy()
         self.flags = np.zeros(self.num_envs, np.uint8)
         self.last_time_steps = [None] * self.num_envs
@@ -202,7 +251,13 @@ class DMCPool:
         h, w = self.obs_size
         self._f[i] = self.envs[i].physics.render(height=h, width=w, camera_id=self.camera_id)
 
+    def _flip(self):
+        self.frames = self._next_set()
+        self._f = self.frames.numpy()
+
     def reset(self, mask=None):
+        self._flip()
+
         def one(i):
             if mask is not None and not mask[i]:
                 self.flags[i] = FLAG_IDLE
@@ -222,6 +277,7 @@ class DMCPool:
         n = self.num_envs
         reward, done = np.zeros(n, np.float64), np.zeros(n, bool)
         motor_action = np.asarray(motor_action, np.float32).reshape(n, -1)
+        self._flip()
 
         def one(i):
             env = self.envs[i]
@@ -306,3 +362,73 @@ class SyntheticDMCSource:
 
     def step(self, motor_action):
         return self._next(), self.flags_step, self._zero, self._false
+
+
+class PinnedFrameSource:
+    """Pre-generated frames in pinned host memory, cycled (``pool`` batches): what a host simulator pool hands over,
+    minus the simulation.  ``kind`` "atari" (two screens per step, gray or RGB; only the sampled rows once the env
+    has called ``set_used_rows``) or "dmc" (one render per step).  Never terminates unless ``done_every`` is set
+    (then env i reports done — and a raw reward of 1 — every ``done_every`` + i % 7 steps: exercises the counters)."""
+
+    def __init__(self, num_envs: int, kind: str = "atari", channels: int = 1, obs_size=(84, 84), pool: int = 2,
+                 seed: int = 7, done_every: int = 0, action_dim: int = 2):
+        self.num_envs, self.kind, self.n_actions, self.action_dim = int(num_envs), kind, 18, action_dim
+        self.raw_shape = (210, 160, channels) if kind == "atari" else (obs_size[0], obs_size[1], 3)
+        self.pool, self.seed, self.done_every = max(2, int(pool)), seed, int(done_every)
+        self.packed_rows, self._rows = False, None
+        self.true_low, self.true_high = -np.ones(action_dim, np.float32), np.ones(action_dim, np.float32)
+        self.t = 0
+        self._steps = np.zeros(self.num_envs, np.int64)
+        self._build()
+
+    def _build(self):
+        h, w, c = self.raw_shape
+        rows = h if self._rows is None else len(self._rows)
+        shape = (self.num_envs, rows, w) if c == 1 else (self.num_envs, rows, w, c)
+        rng = np.random.default_rng(self.seed)
+        per_step = 2 if self.kind == "atari" else 1
+        self.batches = []
+        for _ in range(self.pool * per_step):
+            t = _pinned(shape)
+            t.numpy()[...] = rng.integers(0, 256, shape, dtype=np.uint8)
+            self.batches.append(t)
+
+    def set_used_rows(self, rows) -> None:
+        if self.kind != "atari":
+            return
+        self._rows = np.asarray(rows, np.int64)
+        self.packed_rows = True
+        self._build()
+
+    def frames_consumed(self, events) -> None:  # the pool is read-only: nothing to guard
+        pass
+
+    def _next(self):
+        b = self.batches[self.t % len(self.batches)]
+        self.t += 1
+        return b
+
+    def _flags(self, value, mask):
+        f = np.full(self.num_envs, value, np.uint8)
+        if mask is not None:
+            f[~np.asarray(mask, bool)] = FLAG_IDLE
+        return f
+
+    def reset(self, mask=None):
+        sel = slice(None) if mask is None else np.asarray(mask, bool)
+        self._steps[sel] = 0
+        f = self._next()
+        fl = self._flags(FLAG_FRAME_A | FLAG_HARD_RESET, mask)
+        return (f, f, fl) if self.kind == "atari" else (f, fl)
+
+    def step(self, motor_action):
+        self._steps += 1
+        n = self.num_envs
+        if self.done_every:
+            done = self._steps >= self.done_every + (np.arange(n) % 7)
+            reward = done.astype(np.float64)
+        else:
+            done, reward = np.zeros(n, bool), np.zeros(n, np.float64)
+        if self.kind == "atari":
+            return self._next(), self._next(), self._flags(FLAG_FRAME_A | FLAG_FRAME_B, None), reward, done
+        return self._next(), self._flags(FLAG_FRAME_A, None), reward, done

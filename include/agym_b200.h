@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define AGYM_ABI_VERSION 1
+#define AGYM_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define AGYM_API __attribute__((visibility("default")))
@@ -71,6 +71,12 @@ typedef enum agym_status {
 #define AGYM_OUT_CROP 0          /* (K, f_h, f_w); flexible: padded (K, pad_h, pad_w)         */
 #define AGYM_OUT_MASK 1          /* mask_out: (K, S_h, S_w), zero outside the fovea           */
 #define AGYM_OUT_RESIZE_FULL 2   /* resize_to_full: (K, S_h, S_w)                             */
+
+/* bits of the device error word of agym_observe_flexible (d_err): FOV_RES actions the reference would fail on
+ * (fov_env.py:322-324 stores the action unvalidated; the crop then raises for float bounds or a window larger than
+ * the frame).  The kernels truncate and clamp to [1, S] and report it here instead. */
+#define AGYM_ERR_RES_RANGE 1     /* a FOV_RES action outside [1, obs_size] (or NaN) was clamped   */
+#define AGYM_ERR_RES_FRACTION 2  /* a FOV_RES action with a fractional part was truncated         */
 
 /* sensory_action_type of the flexible fovea (fov_env.py:236-238) */
 #define AGYM_ATYPE_FOV_LOC 0
@@ -152,11 +158,24 @@ AGYM_API int agym_observe_peripheral(const agym_plan *plan, const uint8_t *d_rin
  * top-left corner of a zeroed [N][K][pad_h][pad_w] buffer (pad >= the largest res).
  * Blurred pixels (res rows > fov rows) are within 0.5 LSB + 0.02 of the reference's float value: the W-axis
  * operator runs in 16-bit fixed point (<= 255 * taps / 2^17 LSB from the fp64 weights); windows that the
- * reference does not blur, the mask and the padding are bit exact. */
+ * reference does not blur, the mask and the padding are bit exact.
+ * d_err (may be NULL): one i32 the kernels OR the AGYM_ERR_RES_* bits into; the caller zeroes and reads it. */
 AGYM_API int agym_observe_flexible(const agym_plan *plan, const uint8_t *d_ring, const int32_t *d_head,
                           const double *d_action, const int32_t *d_atype, const uint8_t *d_fov_ctrl,
                           int32_t *d_loc, int32_t *d_res, int variant, int pad_h, int pad_w,
-                          uint8_t *d_out, void *stream);
+                          uint8_t *d_out, int32_t *d_err, void *stream);
+
+/* Replaces RecordWrapper's episode counters (fov_env.py:15-67) and the fov_loc / fov_res trace that
+ * save_transition keeps when record=True (fov_env.py:152-154, 205-207, 253-256, 332-335), for N envs on the device.
+ *   step  (is_reset = 0): ep_len += 1; cum_reward += d_raw_reward (f64 [N], info["raw_reward"]; NULL = 0)
+ *   reset (is_reset = 1): both become 0 for the envs selected by d_reset_mask (u8 [N]; NULL = every env)
+ *   d_ep_len i64 [N], d_cum_reward f64 [N]: the counters, updated in place (info["ep_len"], info["reward"])
+ *   d_trace_row (may be NULL): i32 [N][6] = {fov_loc row, col, fov_res rows, cols, ep_len, valid} for this call;
+ *     valid = 1 on a reset entry of a selected env and on a step whose d_done (u8 [N], NULL = none) is clear
+ *     ("if not done: save_transition").  d_loc / d_res: i32 [N][2] or NULL (written as 0). */
+AGYM_API int agym_record_step(int32_t n_envs, int is_reset, const double *d_raw_reward, const uint8_t *d_done,
+                     const uint8_t *d_reset_mask, int64_t *d_ep_len, double *d_cum_reward, const int32_t *d_loc,
+                     const int32_t *d_res, int32_t *d_trace_row, void *stream);
 
 /* Host-only: the coefficient tables a plan would upload, for inspection and CPU-side tests.
  * agym_table_cv2: OpenCV INTER_LINEAR 11-bit coefficients of one axis (atari_env.py:74);

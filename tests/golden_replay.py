@@ -11,7 +11,7 @@ import numpy as np
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 SCENARIOS = sorted(f[:-4] for f in os.listdir(GOLD)
-                   if f.endswith(".npz") and not f.startswith(("screens_", "primitives")))
+                   if f.endswith(".npz") and not f.startswith(("screens_", "primitives", "record_")))
 
 _screens = {}
 

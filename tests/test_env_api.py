@@ -1,6 +1,8 @@
 """The env layer (host logic) — CPU tests drive the simulator pool with the scripted fake ALE /
 fake physics of oracle/ref_harness.py and compare against what the unmodified reference did
-on the same script (tests/golden); GPU tests run the full drop-in envs against the same fixtures."""
+on the same script (tests/golden); the drop-in env tests run twice: on the GPU box through the CUDA
+path (backend "cuda"), and in the CPU-only container with the C oracle standing in for the kernels
+(backend "oracle", tests/fake_path.py) so that the Python host logic is covered without a GPU."""
 import random
 
 import numpy as np
@@ -9,6 +11,16 @@ import torch
 
 from oracle import ref_harness as rh
 from tests import golden_replay as gr
+
+BACKENDS = ["oracle", pytest.param("cuda", marks=pytest.mark.gpu)]
+
+
+def _backend(monkeypatch, backend):
+    """"oracle": the env classes build tests/fake_path.OraclePath instead of the CUDA engine."""
+    if backend == "oracle":
+        from tests.fake_path import OraclePath
+        monkeypatch.setattr("active_gym_b200.atari_env.PipelinedPath", OraclePath)
+
 
 ATARI = [s for s in gr.SCENARIOS if s.startswith("atari")]
 DMC = [s for s in gr.SCENARIOS if s.startswith("dmc")]
@@ -116,10 +128,11 @@ def _drive_single_env(name, env, z, meta, script):
         assert info["ep_len"] >= 1 and "raw_reward" in info and "reward" in info
 
 
-@pytest.mark.gpu
+@pytest.mark.parametrize("backend", BACKENDS)
 @pytest.mark.parametrize("name", ATARI)
-def test_atari_single_env_dropin_matches_reference(name):
+def test_atari_single_env_dropin_matches_reference(name, backend, monkeypatch):
     import active_gym_b200 as ag
+    _backend(monkeypatch, backend)
     from active_gym_b200.sources import ALEPool
     z, meta = gr.load(name)
     script = _script(meta)
@@ -145,10 +158,11 @@ def test_atari_single_env_dropin_matches_reference(name):
             assert np.abs(obs * 255.0 - want).max() <= 0.5 + 1e-2, (name, i)
 
 
-@pytest.mark.gpu
+@pytest.mark.parametrize("backend", BACKENDS)
 @pytest.mark.parametrize("name", DMC)
-def test_dmc_single_env_dropin_matches_reference(name):
+def test_dmc_single_env_dropin_matches_reference(name, backend, monkeypatch):
     import active_gym_b200 as ag
+    _backend(monkeypatch, backend)
     from active_gym_b200.sources import DMCPool
     z, meta = gr.load(name)
     script = rh.ScreenScript(gr.screens("dmc"))
