@@ -7,6 +7,8 @@ takes an extra ``num_envs`` (batched, uint8 CUDA observations) and defaults to t
 drop-in that returns the reference's types.
 """
 from .engine import LUMA_DMC, LUMA_RGB, ObservationPath  # noqa: F401
+from .pipeline import PipelinedPath  # noqa: F401
+from .vector import FovealVectorEnv, ShardedVecEnv  # noqa: F401
 from .atari_env import (  # noqa: F401
     AtariBaseEnv, AtariEnvArgs, AtariFixedFovealEnv, AtariFixedFovealPeripheralEnv, AtariFlexibleFovealEnv, AtariVecEnv,
 )
@@ -22,5 +24,6 @@ __all__ = [
     "AtariBaseEnv", "AtariFixedFovealEnv", "AtariFlexibleFovealEnv", "AtariFixedFovealPeripheralEnv", "AtariEnvArgs",
     "DMCBaseEnv", "DMCFixedFovealEnv", "DMCFlexibleFovealEnv", "DMCFixedFovealPeripheralEnv", "DMCEnvArgs",
     "RecordWrapper", "FixedFovealEnv", "FlexibleFovealEnv", "FlexibleFovealEnvActionType", "FixedFovealPeripheralEnv",
-    "AtariVecEnv", "DMCVecEnv", "SingleEnvAdapter", "ObservationPath", "LUMA_RGB", "LUMA_DMC",
+    "AtariVecEnv", "DMCVecEnv", "SingleEnvAdapter", "ObservationPath", "PipelinedPath", "FovealVectorEnv", "ShardedVecEnv",
+    "LUMA_RGB", "LUMA_DMC",
 ]

@@ -39,7 +39,7 @@ class AtariEnvArgs:
             self.__setattr__(k, v)
 
 
-def _path_from_args(args, num_envs, raw_shape, luma, device, host_source: bool) -> PipelinedPath:
+def _path_from_args(args, num_envs, obs_size, raw_shape, luma, device, host_source: bool) -> PipelinedPath:
     """The per-GPU engine of an env batch.  ``args.shards`` (default: 8 for host frame sources, whose copies
     should overlap the kernels; 1 for device-resident sources) cuts the batch into env-index shards with their own
     streams (pipeline.PipelinedPath)."""
@@ -48,7 +48,7 @@ def _path_from_args(args, num_envs, raw_shape, luma, device, host_source: bool) 
     if shards is None:
         shards = 8 if host_source and num_envs >= 64 else 1
     return PipelinedPath(
-        num_envs, args.frame_stack, tuple(args.obs_size), raw_shape, shards=shards, luma=luma,
+        num_envs, args.frame_stack, obs_size, raw_shape, shards=shards, luma=luma,
         fov_size=tuple(fov) if fov is not None else None,
         fov_init_loc=getattr(args, "fov_init_loc", (0, 0)),
         sensory_action_mode=getattr(args, "sensory_action_mode", "absolute"),
@@ -69,10 +69,14 @@ class _VecBase(Env):
         self.frame_stack = args.frame_stack
         self.action_repeat = args.action_repeat
         self.obs_size = tuple(args.obs_size)
+        if getattr(args, "cv2_dsize_quirk", False):
+            # atari_env.py:74 hands obs_size = (h, w) to cv2.resize as dsize = (width, height): a non-square obs_size
+            # comes out transposed, (w, h), in the reference.  Off by default (obs_size means (h, w) here).
+            self.obs_size = self.obs_size[::-1]
         self.clip_reward = args.clip_reward
         self.source = source
         host_source = not hasattr(source, "device")
-        self.path = _path_from_args(args, self.num_envs, tuple(source.raw_shape), luma,
+        self.path = _path_from_args(args, self.num_envs, self.obs_size, tuple(source.raw_shape), luma,
                                     device or getattr(args, "device", None), host_source)
         self.device = self.path.device
         self.host_obs = bool(getattr(args, "host_obs", False))

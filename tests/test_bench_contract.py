@@ -28,7 +28,13 @@ def test_reference_arm_prints_one_json_line_with_the_contract_keys():
     assert d["higher_is_better"] is True and d["steps"] == 2 and d["warmup"] == 1 and d["value"] > 0
     assert d["config"]["workload"] == "atari_peripheral"
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "sample" in cb
+    # "reference" = the unmodified reference from baseline/_ref (or /root/reference) under the simulator stubs; "port" otherwise
+    assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == d["value"] and "sample" in cb
+    have_ref = os.path.isfile(os.path.join(ROOT, "baseline", "_ref", "active_gym", "fov_env.py")) or os.path.isdir("/root/reference")
+    assert cb["kind"] == ("reference" if have_ref else "port")
+    sys.path.insert(0, ROOT)
+    import bench
+    assert d["config"] == bench.config_for("atari_peripheral", 16384, 1)   # the b200 arm prints the same object
     assert d["e2e"] == {"value": d["value"], "unit": "obs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 

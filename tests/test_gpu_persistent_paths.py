@@ -184,29 +184,120 @@ def test_flexible_v3_other_stack_depths_and_fovea_shapes(K, fov):
         assert np.array_equal(got[sharp], want[sharp])
 
 
-def test_host_pipeline_shards_equal_unsharded_path():
-    from active_gym_b200.hostpipe import HostPipelinedEnv
+@pytest.mark.parametrize("shards,pinned", [(7, True), (3, False), (1, True)])
+def test_pipelined_path_host_inputs_match_the_oracle(shards, pinned):
+    """PipelinedPath (env-index shards on their own streams, host frames / actions in, pinned observations out) against
+    the ORACLE: full host frames (strided packed copy when pinned), then frames that already hold only the sampled rows."""
+    from active_gym_b200.pipeline import PipelinedPath
     rng = np.random.default_rng(9)
     n, K = 203, 4  # not a multiple of the shard count
     kw = dict(fov_size=(30, 30), sensory_action_mode="relative", sensory_action_space=(-10.0, 10.0), peripheral_res=(20, 20))
-    env = HostPipelinedEnv(n, K, S, (210, 160, 1), kind="atari", wrapper="peripheral", shards=7, **kw)
+    pp = PipelinedPath(n, K, S, (210, 160, 1), shards=shards, **kw)
+    assert pp.run == (5, 3, 4)
+    ring, head = orc.new_state(n, K, S)
+    loc = np.zeros((n, 2), np.int32)
+    rows = pp.used_rows
+
+    def host(a):
+        t = torch.from_numpy(np.ascontiguousarray(a))
+        return t.pin_memory() if pinned else t
+
+    for step in range(5):
+        fa, fb = _frames(rng, n), _frames(rng, n)
+        fl = np.full(n, 5, np.uint8) if step == 0 else _flags(rng, n)
+        if step % 2:
+            pp.ingest_atari(host(fa[:, rows]), host(fb[:, rows]), fl, packed=True)
+        else:
+            pp.ingest_atari(host(fa), host(fb), fl)
+        orc.ingest_atari(fa, fb, fl, ring, head)
+        if step == 0:
+            out, (h_obs, h_loc, _) = pp.observe_peripheral(None, ctrl="reset", host_out=True)
+        else:
+            a = rng.integers(-10, 11, (n, 2)).astype(np.float64)
+            orc.update_loc(a, loc, obs_size=S, fov_size=(30, 30), relative=True, lo=-10.0, hi=10.0)
+            out, (h_obs, h_loc, _) = pp.observe_peripheral(a, host_out=True)
+        pp.sync()
+        assert np.array_equal(_np(pp.ring), ring) and np.array_equal(_np(pp.head), head), step
+        assert np.array_equal(h_loc.numpy(), loc), step
+        want = orc.observe_peripheral(ring, head, loc, (30, 30), (20, 20))
+        assert np.abs(h_obs.numpy().astype(np.float64) - want).max() <= TOL, step
+        assert np.array_equal(h_obs.numpy(), _np(out)), step
+    assert pp.h2d_bytes > 0 and pp.d2h_bytes > 0
+
+
+def test_pipelined_path_device_inputs_equal_single_path_and_record_counters():
+    """Device-resident inputs: the shards read slices of the caller's tensors (no copies); results equal one unsharded
+    ObservationPath bit for bit; the RecordWrapper counters / trace row follow k_record_step's contract."""
+    from active_gym_b200.pipeline import PipelinedPath
+    rng = np.random.default_rng(10)
+    n, K = 130, 4
+    kw = dict(fov_size=(30, 30), sensory_action_mode="absolute")
+    pp = PipelinedPath(n, K, S, (210, 160, 1), shards=4, **kw)
     ref = _path(n, K, **kw)
-    hf = env.alloc_host_frames()
-    for t in hf:
-        t.numpy()[...] = _frames(rng, n)
-    obs, loc = env.reset_host(hf)
-    ref.ingest_atari(hf[0].numpy(), hf[0].numpy(), np.full(n, 5, np.uint8))
-    want = ref.observe_peripheral(None, ctrl="reset")
-    assert np.array_equal(obs.numpy(), _np(want)) and np.array_equal(loc.numpy(), _np(ref.loc))
-    for step in range(3):
-        for t in hf:
-            t.numpy()[...] = _frames(rng, n)
-        a = rng.integers(-10, 11, (n, 2)).astype(np.float64)
-        obs, loc = env.step_host(hf, a)
-        ref.ingest_atari(hf[0].numpy(), hf[1].numpy(), np.full(n, 3, np.uint8))
-        want = ref.observe_peripheral(a)
-        assert np.array_equal(obs.numpy(), _np(want)), step
-        assert np.array_equal(loc.numpy(), _np(ref.loc)), step
+    trace = torch.zeros((n, 6), dtype=torch.int32, device="cuda")
+    want_len, want_cum = np.zeros(n, np.int64), np.zeros(n)
+    for step in range(4):
+        fa = torch.from_numpy(_frames(rng, n)).cuda()
+        fb = torch.from_numpy(_frames(rng, n)).cuda()
+        fl = torch.from_numpy(np.full(n, 5, np.uint8) if step == 0 else _flags(rng, n)).cuda()
+        a = torch.from_numpy(rng.uniform(-5, 60, (n, 2))).cuda()
+        at = torch.from_numpy(rng.integers(0, 2, n).astype(np.int32)).cuda()
+        a = torch.where(at[:, None] == 1, torch.randint(20, 51, (n, 2), device="cuda").double(), a)
+        pp.ingest_atari(fa, fb, fl)
+        ref.ingest_atari(fa, fb, fl)
+        got = pp.observe_flexible(a, at, variant="mask")
+        want = ref.observe_flexible(a, at, variant="mask")
+        assert torch.equal(got, want) and torch.equal(pp.loc, ref.loc) and torch.equal(pp.res, ref.res), step
+        assert torch.equal(pp.ring, ref.ring) and torch.equal(pp.head, ref.head), step
+        rew = rng.uniform(-1, 1, n)
+        done = rng.random(n) < 0.3
+        pp.record_step(raw_reward=rew, done=done, trace_row=trace, with_res=True)
+        want_len += 1
+        want_cum += rew
+        assert np.array_equal(_np(pp.ep_len), want_len) and np.array_equal(_np(pp.cum_reward), want_cum)
+        t = _np(trace)
+        assert np.array_equal(t[:, 0:2], _np(pp.loc)) and np.array_equal(t[:, 2:4], _np(pp.res))
+        assert np.array_equal(t[:, 4], want_len) and np.array_equal(t[:, 5], (~done).astype(np.int32))
+        mask = rng.random(n) < 0.2
+        pp.record_step(reset_mask=mask, is_reset=True)
+        want_len[mask], want_cum[mask] = 0, 0
+        assert np.array_equal(_np(pp.ep_len), want_len) and np.array_equal(_np(pp.cum_reward), want_cum)
+    assert pp.read_errors() == 0
+
+
+def test_flexible_device_actions_report_invalid_windows_in_the_error_word():
+    """FOV_RES actions the reference would fail on (fov_env.py:322-324: fractional or larger than the frame) are
+    clamped by the kernels and reported: ObservationPath.read_errors, and the env raises like the reference."""
+    import active_gym_b200 as ag
+    from active_gym_b200 import _lib
+    from active_gym_b200.sources import SyntheticAtariSource
+    n = 40
+    p = _path(n, 4, fov_size=(30, 30), sensory_action_mode="absolute")
+    p.ingest_atari(np.zeros((n, 210, 160), np.uint8), np.zeros((n, 210, 160), np.uint8), np.full(n, 5, np.uint8))
+    at = torch.ones(n, dtype=torch.int32, device="cuda")
+    ok = torch.full((n, 2), 40.0, dtype=torch.float64, device="cuda")
+    p.observe_flexible(ok, at, variant="mask")
+    assert p.read_errors() == 0
+    bad = ok.clone(); bad[3, 0] = 90.0
+    p.observe_flexible(bad, at, variant="mask")
+    assert p.read_errors() == _lib.ERR_RES_RANGE and p.read_errors() == 0
+    assert _np(p.res)[3].tolist() == [84, 40]
+    bad = ok.clone(); bad[7, 1] = 33.5; bad[9, 0] = float("nan")
+    p.observe_flexible(bad, at, variant="crop", pad=(84, 84))
+    assert p.read_errors() == (_lib.ERR_RES_RANGE | _lib.ERR_RES_FRACTION)
+    assert _np(p.res)[7].tolist() == [40, 33] and _np(p.res)[9].tolist() == [1, 40]
+    # through the env: device-tensor actions are validated after the fact (at the latest one step later)
+    args = ag.AtariEnvArgs(game="boxing", seed=0, obs_size=(84, 84), fov_size=(30, 30), fov_init_loc=(0, 0),
+                           sensory_action_mode="absolute", mask_out=True)
+    env = ag.AtariFlexibleFovealEnv(args, num_envs=n, source=SyntheticAtariSource(n, device="cuda"))
+    env.reset()
+    act = {"motor_action": np.zeros(n, np.int64), "sensory_action": bad, "sensory_action_type": at}
+    with pytest.raises(ValueError, match="FOV_RES"):
+        for _ in range(3):
+            env.step(act)
+            torch.cuda.synchronize()
+    with pytest.raises(ValueError, match="FOV_RES"):   # host actions are checked before the launch
+        env.step({"motor_action": np.zeros(n, np.int64), "sensory_action": np.full((n, 2), 99.0), "sensory_action_type": np.ones(n, np.int64)})
 
 
 @pytest.mark.parametrize("ch,n", [(1, 700), (3, 40)])
@@ -229,24 +320,11 @@ def test_packed_rows_ingest_is_bit_identical(ch, n):
         assert torch.equal(a.pcache, b.pcache), step
 
 
-def test_host_pipeline_packed_h2d_equals_full_frames():
-    from active_gym_b200.hostpipe import HostPipelinedEnv, periodic_run
-    rng = np.random.default_rng(13)
-    n, K = 150, 4
-    kw = dict(fov_size=(30, 30), sensory_action_mode="relative", sensory_action_space=(-10.0, 10.0), peripheral_res=(20, 20))
-    packed = HostPipelinedEnv(n, K, S, (210, 160, 1), kind="atari", wrapper="peripheral", shards=4, packed_h2d=True, **kw)
-    full = HostPipelinedEnv(n, K, S, (210, 160, 1), kind="atari", wrapper="peripheral", shards=3, packed_h2d=False, **kw)
-    assert packed.run == (5, 3, 4) and full.run is None
-    assert packed.h2d_bytes_per_step < 0.81 * full.h2d_bytes_per_step
+def test_periodic_run_detection():
+    from active_gym_b200.pipeline import periodic_run
+    p = _path(4, 4, fov_size=(30, 30))
+    assert periodic_run(p.used_rows, 210) == (5, 3, 4)
     assert periodic_run(np.arange(84), 84) is None  # nothing to skip: no packed mode
-    hp, hf = packed.alloc_host_frames(), full.alloc_host_frames()
-    for step in range(4):
-        for tp, tf in zip(hp, hf):
-            tf.numpy()[...] = _frames(rng, n)
-            tp.numpy()[...] = tf.numpy()
-        a = rng.integers(-10, 11, (n, 2)).astype(np.float64)
-        (op, lp), (of, lf) = (packed.reset_host(hp), full.reset_host(hf)) if step == 0 else (packed.step_host(hp, a), full.step_host(hf, a))
-        assert np.array_equal(op.numpy(), of.numpy()) and np.array_equal(lp.numpy(), lf.numpy()), step
 
 
 @pytest.mark.parametrize("obs,fov,periph", [((64, 64), (20, 24), (16, 16)), ((96, 96), (30, 30), (24, 20)), ((84, 84), (30, 30), (21, 28))])

@@ -1,0 +1,96 @@
+"""gymnasium.vector.VectorEnv-shaped adapter and the multi-GPU front end.  Backend "oracle"
+runs the Python logic in the CPU container (tests/fake_path.py), backend "cuda" the same through the kernels."""
+import numpy as np
+import pytest
+import torch
+
+from tests.test_env_api import BACKENDS, _backend
+
+
+def _args(**kw):
+    import active_gym_b200 as ag
+    base = dict(game="boxing", seed=0, obs_size=(84, 84), fov_size=(30, 30), fov_init_loc=(4, 6),
+                sensory_action_mode="relative", sensory_action_space=(-10.0, 10.0), peripheral_res=(20, 20))
+    base.update(kw)
+    return ag.AtariEnvArgs(**base)
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_vector_env_surface_spaces_and_autoreset(backend, monkeypatch):
+    import active_gym_b200 as ag
+    from active_gym_b200.sources import PinnedFrameSource
+    _backend(monkeypatch, backend)
+    n = 8
+    env = ag.AtariFixedFovealPeripheralEnv(_args(), num_envs=n, source=PinnedFrameSource(n, pool=3, done_every=2))
+    vec = ag.FovealVectorEnv(env)
+    # the attributes gymnasium.vector.VectorEnv documents
+    assert vec.num_envs == n and vec.is_vector_env and not vec.closed
+    assert vec.single_observation_space.shape == (4, 84, 84) and vec.observation_space.shape == (n, 4, 84, 84)
+    sa = vec.single_action_space["sensory_action"]
+    assert sa.shape == (2,) and sa.low.tolist() == [-10, -10] and sa.high.tolist() == [10, 10]
+    assert vec.action_space["sensory_action"].shape == (n, 2) and vec.action_space["motor_action"].shape == (n,)
+    a = vec.action_space.sample()
+    assert a["sensory_action"].shape == (n, 2) and a["motor_action"].shape == (n,)
+    # the reference's own (degenerate, one-dimensional) declaration stays available (fov_env.py:125-129)
+    ref_space = ag.FovealVectorEnv(env, fix_sensory_space=False).single_action_space["sensory_action"]
+    assert ref_space.shape == (1,)
+    obs, info = vec.reset(seed=3)
+    assert tuple(obs.shape) == (n, 4, 84, 84) and [int(v) for v in info["fov_loc"][0]] == [4, 6]
+    assert vec.get_attr("fov_size") == (30, 30) and vec.call("variant") == "crop"
+    seen_final = False
+    for step in range(6):
+        obs, r, term, trunc, info = vec.step({"motor_action": np.zeros(n, np.int64), "sensory_action": np.full((n, 2), 3.0)})
+        assert tuple(obs.shape) == (n, 4, 84, 84) and term.dtype == bool and trunc.dtype == bool and not trunc.any()
+        ep_len = np.asarray(torch.as_tensor(info["ep_len"]).cpu())
+        loc = np.asarray(torch.as_tensor(info["fov_loc"]).cpu())
+        if term.any():
+            seen_final = True
+            k = int(term.sum())
+            assert tuple(info["final_observation"].shape) == (k, 4, 84, 84) and info["_final_observation"].tolist() == term.tolist()
+            assert np.asarray(torch.as_tensor(info["final_info"]["ep_len"]).cpu()).min() >= 2
+            assert (ep_len[term] == 0).all() and (loc[term] == [4, 6]).all()       # restarted at once, like SyncVectorEnv
+            assert (ep_len[~term] > 0).all()
+        assert list(vec.envs[1].fov_loc) == loc[1].tolist()
+    assert seen_final
+    vec.close()
+    assert vec.closed
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_sharded_vec_env_equals_one_batch(backend, monkeypatch):
+    """Global batch over several 'devices' (the same GPU twice on a 1-GPU box; env-index blocks from sharding.env_shard)
+    == one unsharded env on the same frames."""
+    import active_gym_b200 as ag
+    from active_gym_b200.sources import PinnedFrameSource
+    _backend(monkeypatch, backend)
+    n = 11
+    dev = "cuda:0" if backend == "cuda" else "cpu"
+    full = PinnedFrameSource(n, pool=3, seed=21)
+
+    class Block:   # rows [lo, hi) of the full source's batches
+        def __init__(s, lo, hi):
+            s.lo, s.hi, s.t, s.raw_shape, s.n_actions = lo, hi, 0, full.raw_shape, full.n_actions
+        def _next(s):
+            b = full.batches[s.t % len(full.batches)][s.lo:s.hi]; s.t += 1; return b
+        def reset(s, mask=None):
+            f = s._next(); return f, f, np.full(s.hi - s.lo, 5, np.uint8)
+        def step(s, a):
+            return s._next(), s._next(), np.full(s.hi - s.lo, 3, np.uint8), np.zeros(s.hi - s.lo), np.zeros(s.hi - s.lo, bool)
+
+    args = _args(shards=2)
+    sh = ag.ShardedVecEnv(lambda m, d, lo, hi: ag.AtariFixedFovealPeripheralEnv(args, num_envs=m, source=Block(lo, hi), device=d),
+                          n, devices=[dev, dev, dev])
+    assert sh.ranges == [(0, 4), (4, 8), (8, 11)]
+    one = ag.AtariFixedFovealPeripheralEnv(args, num_envs=n, source=Block(0, n), device=dev)
+    o_sh, i_sh = sh.reset()
+    o_one, i_one = one.reset()
+    rng = np.random.default_rng(1)
+    for step in range(3):
+        act = {"motor_action": np.zeros(n, np.int64), "sensory_action": rng.integers(-10, 11, (n, 2)).astype(np.float64)}
+        o_sh, r, d, t, i_sh = sh.step(act)
+        o_one, r1, d1, t1, i_one = one.step(act)
+        assert torch.equal(ag.ShardedVecEnv.gather(o_sh, dev), o_one), step
+        assert torch.equal(torch.cat([torch.as_tensor(v) for v in i_sh["fov_loc"]]) if isinstance(i_sh["fov_loc"], list)
+                           else torch.as_tensor(i_sh["fov_loc"]), torch.as_tensor(i_one["fov_loc"])), step
+        assert r.shape == (n,) and d.shape == (n,)
+    sh.close()
