@@ -270,7 +270,7 @@ constexpr int kIngestThreads = kThreads + 32;
 // and never row 5m+2.  The frames are then viewed as a 4-D tensor [env][period of 5 rows][row in period][row bytes]
 // and a unit's rows arrive as TWO tiled tensor copies per frame (boxes of 2 rows x R/2 periods at row 0 and at
 // row 3 of the period): the unsampled fifth of every frame never leaves HBM, with as few copies as before.
-template <int RAW_W, int S_W, int CH, bool TM, int NS, int ROWS = 0>  // RAW_W: BYTES per raw row (pixels * CH) when baked in; NS: stages; ROWS: rows per segment if fixed
+template <int RAW_W, int S_W, int CH, bool TM, int NS>  // RAW_W: BYTES per raw row (pixels * CH) when baked in; NS: stages
 __global__ void __launch_bounds__(kIngestThreads, 3) k_ingest_atari_tma(const __grid_constant__ DevPlan p,
                                                                         const uint8_t *__restrict__ fa,
                                                                         const uint8_t *__restrict__ fb,
@@ -459,13 +459,8 @@ __global__ void __launch_bounds__(kIngestThreads, 3) k_ingest_atari_tma(const __
                     }
                     *reinterpret_cast<uint16_t *>(dst) = (uint16_t)(((m0 + 2u) >> 2) | (((m1 + 2u) >> 2) << 8));
                 };
-                if (ROWS > 0) {   // every row segment has exactly ROWS rows: no loop bookkeeping, no odd-row remainder
-#pragma unroll
-                    for (int r = 0; r < ROWS; ++r) row_both(rw[r], o + r * S_w);
-                } else {
 #pragma unroll 2
-                    for (int yy = yy_begin; yy < yy_end; ++yy, ++rw, o += S_w) row_both(*rw, o);
-                }
+                for (int yy = yy_begin; yy < yy_end; ++yy, ++rw, o += S_w) row_both(*rw, o);
             } else {  // resets / early game-over: one frame or none
                 for (int yy = yy_begin; yy < yy_end; ++yy, ++rw, o += S_w) {
                     const int4 t = *rw;
@@ -725,10 +720,6 @@ bool encode_period5(CUtensorMap *m, const uint8_t *frames, int rowb, int raw_h, 
     return enc(m, dt, 4, const_cast<uint8_t *>(frames), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
-// AGYM_INGEST_STAGES=3: three stages in the TMA ingest ring (tuning)
-const int g_stages = getenv("AGYM_INGEST_STAGES") ? atoi(getenv("AGYM_INGEST_STAGES")) : 0;
-// AGYM_NO_ROWS=1: runtime row loop in the gray tensor-copy ingest (A/B)
-const bool g_no_rows = getenv("AGYM_NO_ROWS") != nullptr;
 // AGYM_NO_TM=1: contiguous bulk copies instead of the strided tensor copies in the TMA ingest kernel (A/B)
 const bool g_disable_tm = getenv("AGYM_NO_TM") != nullptr;
 }  // namespace
@@ -775,8 +766,8 @@ cudaError_t launch_ingest_atari(const DevPlan &p, const uint8_t *fa, const uint8
         const int R = p.S_h / units;
         const size_t stage = tm ? a16(2 * (2 * (((size_t)R * rowb + 127) & ~size_t(127)) + 128)) : a16(2 * ((size_t)span_rows * rowb + 16));
         const bool std_geom = p.raw_w == 160 && p.S_w == 84;
-        // stages of the shared-memory ring: the gap-free gray stages are small enough for three at 3 CTAs per SM
-        const int ns = (tm && std_geom && (g_stages ? g_stages == 3 : (p.raw_c == 1 && units >= 3))) ? 3 : 2;
+        // stages of the shared-memory ring: the gap-free gray stages of a 3-unit split are small enough for three at 3 CTAs per SM
+        const int ns = (tm && std_geom && p.raw_c == 1 && units >= 3) ? 3 : 2;
         size_t fs = (tm ? 128 : 0) + ns * stage + a16(p.plane + 16) + 16 * (size_t)p.S_h + 8 * (size_t)((units + 1) & ~1);
         if (pcache) fs += sizeof(float) * ((size_t)p.S_h * p.p_w + (size_t)p.p_w * 24 + (size_t)p.p_h * p.sq_h.taps + (size_t)p.p_h);
         int dev = 0, sms = 148, occ = 1;
@@ -790,14 +781,12 @@ cudaError_t launch_ingest_atari(const DevPlan &p, const uint8_t *fa, const uint8
             p, fa, fb, flags, ring, head, pcache, units, span_rows, tma, tmb);                                      \
     }
         if (p.raw_c == 3) {
-            if (std_geom && tm && ns == 3) AGYM_LAUNCH_TMA(480, 84, 3, true, 3)
-            else if (std_geom && tm) AGYM_LAUNCH_TMA(480, 84, 3, true, 2)
+            if (std_geom && tm) AGYM_LAUNCH_TMA(480, 84, 3, true, 2)
             else if (std_geom) AGYM_LAUNCH_TMA(480, 84, 3, false, 2)
             else if (tm) AGYM_LAUNCH_TMA(0, 0, 3, true, 2)
             else AGYM_LAUNCH_TMA(0, 0, 3, false, 2)
         } else {
             if (std_geom && tm && ns == 3) AGYM_LAUNCH_TMA(160, 84, 1, true, 3)
-            else if (std_geom && tm && units == 2 && p.S_h == 84 && !g_no_rows) AGYM_LAUNCH_TMA(160, 84, 1, true, 2, 7)
             else if (std_geom && tm) AGYM_LAUNCH_TMA(160, 84, 1, true, 2)
             else if (std_geom) AGYM_LAUNCH_TMA(160, 84, 1, false, 2)
             else if (tm) AGYM_LAUNCH_TMA(0, 0, 1, true, 2)

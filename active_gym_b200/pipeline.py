@@ -82,7 +82,7 @@ class PipelinedPath:
     def __init__(self, n_envs: int, frame_stack: int, obs_size, raw_shape, shards: int = 1, device=None,
                  luma: Sequence[int] = LUMA_RGB, fov_size=None, fov_init_loc=(0, 0), sensory_action_mode: str = "absolute",
                  sensory_action_space=(0.0, 0.0), peripheral_res=None, cache_peripheral: bool = True,
-                 packed_h2d: bool = True):
+                 packed_h2d: bool = True, side_streams: bool = False):
         if not torch.cuda.is_available():
             raise RuntimeError("active_gym_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
@@ -118,8 +118,9 @@ class PipelinedPath:
                                              res=self.res[lo:hi], pcache=None if self.pcache is None else self.pcache[lo:hi],
                                              err=self.err))
                 for lo, hi in self.ranges]
-            # one shard: work is issued on the caller's stream; several: one side stream each
-            self.streams = [torch.cuda.Stream(device=dev) for _ in self.ranges] if len(self.ranges) > 1 else None
+            # one shard: work is issued on the caller's stream (unless `side_streams`: a host-driven env group keeps its
+            # own stream so that two groups overlap each other's copies); several: one side stream each
+            self.streams = [torch.cuda.Stream(device=dev) for _ in self.ranges] if (len(self.ranges) > 1 or side_streams) else None
             self._fork_ev = torch.cuda.Event()
             self._join_evs = [torch.cuda.Event() for _ in self.ranges]
         rh, rw, rc = self.raw_shape

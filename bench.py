@@ -35,6 +35,10 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
+# The e2e leg drives several copy streams per GPU (2 env groups x shards, both directions).  With the default of 8
+# hardware work queues, streams created later alias onto the same queue and falsely serialise each other's copies
+# (measured: the same pipeline 18.8 ms / step on fresh streams, 22-25 ms once more than 8 streams had been created).
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 import numpy as np  # noqa: E402
 
@@ -796,7 +800,7 @@ def main():
     ap.add_argument("--envs", type=int, default=None, help="envs per GPU (default: the BASELINE config's N)")
     ap.add_argument("--only", action="store_true", help="time only --workload (no `workloads` / `strong_scaling` extras)")
     ap.add_argument("--other-steps", type=int, default=20, help="timed steps of each extra workload")
-    ap.add_argument("--shards", type=int, default=8, help="env-index shards (streams) per env group of the e2e leg")
+    ap.add_argument("--shards", type=int, default=2, help="env-index shards (streams) per env group of the e2e leg")
     ap.add_argument("--cpu-steps-per-proc", type=int, default=0, help="env-steps per CPU process and sample (0 = calibrate from --cpu-seconds)")
     ap.add_argument("--cpu-seconds", type=float, default=1.5, help="wall seconds of the bounded CPU sample (x host cores = CPU work)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -26,7 +26,7 @@ class OraclePath:
 
     def __init__(self, n_envs, frame_stack, obs_size, raw_shape, shards=1, device=None, luma=orc.LUMA_RGB, fov_size=None,
                  fov_init_loc=(0, 0), sensory_action_mode="absolute", sensory_action_space=(0.0, 0.0), peripheral_res=None,
-                 cache_peripheral=True, packed_h2d=True):
+                 cache_peripheral=True, packed_h2d=True, side_streams=False):
         self.device = torch.device("cpu")
         self.n_envs, self.frame_stack = int(n_envs), int(frame_stack)
         self.obs_size = tuple(int(v) for v in obs_size)
