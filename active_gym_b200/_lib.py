@@ -21,6 +21,7 @@ FOV_APPLY, FOV_RESET, FOV_KEEP = 0, 1, 2
 OUT_CROP, OUT_MASK, OUT_RESIZE_FULL = 0, 1, 2
 ATYPE_FOV_LOC, ATYPE_FOV_RES = 0, 1
 ERR_RES_RANGE, ERR_RES_FRACTION = 1, 2
+DTYPE_F32, DTYPE_F16, DTYPE_BF16 = 0, 1, 2
 
 # the symbols include/agym_b200.h declares; tests check that the .so exports every one
 EXPORTS = (
@@ -68,9 +69,9 @@ def lib() -> C.CDLL:
     L.agym_ingest_atari_packed.argtypes = [vp] * 8
     L.agym_plan_used_rows.argtypes = [vp, vp, i32]
     L.agym_stack.argtypes = [vp] * 5
-    L.agym_observe_fixed.argtypes = [vp, vp, vp, vp, vp, vp, i32, vp, vp]
-    L.agym_observe_peripheral.argtypes = [vp] * 9
-    L.agym_observe_flexible.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp, vp, vp]
+    L.agym_observe_fixed.argtypes = [vp, vp, vp, vp, vp, vp, i32, vp, vp, i32, vp]
+    L.agym_observe_peripheral.argtypes = [vp] * 9 + [i32, vp]
+    L.agym_observe_flexible.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp, vp, vp, i32, vp]
     L.agym_record_step.argtypes = [i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     L.agym_synth_frames.argtypes = [vp, sz, u64, vp]
     L.agym_normalize.argtypes = [vp, sz, i32, vp, vp]

@@ -485,32 +485,52 @@ static int check_fov_args(const agym_plan *plan, const void *ring, const void *h
     return AGYM_OK;
 }
 
+static int check_norm_args(const void *d_out, size_t out_bytes, const void *d_out_norm, int norm_dtype) {
+    if (!d_out_norm) return AGYM_OK;
+    if (norm_dtype < AGYM_DTYPE_F32 || norm_dtype > AGYM_DTYPE_BF16) return AGYM_ERR_INVALID_ARG;
+    if (out_bytes % 4 != 0 || (reinterpret_cast<uintptr_t>(d_out_norm) & 15) || (reinterpret_cast<uintptr_t>(d_out) & 15))
+        return AGYM_ERR_INVALID_ARG;
+    return AGYM_OK;
+}
+
 int agym_observe_fixed(const agym_plan *plan, const uint8_t *d_ring, const int32_t *d_head, const double *d_action,
-                       const uint8_t *d_fov_ctrl, int32_t *d_loc, int variant, uint8_t *d_out, void *stream) {
-    const int v = check_fov_args(plan, d_ring, d_head, d_action, d_fov_ctrl, d_loc, d_out);
+                       const uint8_t *d_fov_ctrl, int32_t *d_loc, int variant, uint8_t *d_out, void *d_out_norm,
+                       int norm_dtype, void *stream) {
+    int v = check_fov_args(plan, d_ring, d_head, d_action, d_fov_ctrl, d_loc, d_out);
     if (v != AGYM_OK) return v;
     if (variant < AGYM_OUT_CROP || variant > AGYM_OUT_RESIZE_FULL) return AGYM_ERR_INVALID_ARG;
-    return ret(launch_observe_fixed(plan->dev, d_ring, d_head, d_action, d_fov_ctrl, d_loc, variant, d_out, as_stream(stream)));
+    const agym_config &c = plan->cfg;
+    const size_t bytes = static_cast<size_t>(c.n_envs) * c.frame_stack * (variant == AGYM_OUT_CROP ? c.fov_h * c.fov_w : c.obs_h * c.obs_w);
+    if ((v = check_norm_args(d_out, bytes, d_out_norm, norm_dtype)) != AGYM_OK) return v;
+    return ret(launch_observe_fixed(plan->dev, d_ring, d_head, d_action, d_fov_ctrl, d_loc, variant, d_out, d_out_norm, norm_dtype,
+                                    as_stream(stream)));
 }
 
 int agym_observe_peripheral(const agym_plan *plan, const uint8_t *d_ring, const int32_t *d_head, const float *d_pcache,
                             const double *d_action, const uint8_t *d_fov_ctrl, int32_t *d_loc, uint8_t *d_out,
-                            void *stream) {
-    const int v = check_fov_args(plan, d_ring, d_head, d_action, d_fov_ctrl, d_loc, d_out);
+                            void *d_out_norm, int norm_dtype, void *stream) {
+    int v = check_fov_args(plan, d_ring, d_head, d_action, d_fov_ctrl, d_loc, d_out);
     if (v != AGYM_OK) return v;
     if (plan->cfg.periph_h == 0) return AGYM_ERR_INVALID_ARG;
-    return ret(launch_observe_peripheral(plan->dev, &plan->expand_std, d_ring, d_head, d_pcache, d_action, d_fov_ctrl, d_loc, d_out, as_stream(stream)));
+    const agym_config &c = plan->cfg;
+    if ((v = check_norm_args(d_out, static_cast<size_t>(c.n_envs) * c.frame_stack * c.obs_h * c.obs_w, d_out_norm, norm_dtype)) != AGYM_OK) return v;
+    return ret(launch_observe_peripheral(plan->dev, &plan->expand_std, d_ring, d_head, d_pcache, d_action, d_fov_ctrl, d_loc, d_out,
+                                         d_out_norm, norm_dtype, as_stream(stream)));
 }
 
 int agym_observe_flexible(const agym_plan *plan, const uint8_t *d_ring, const int32_t *d_head, const double *d_action,
                           const int32_t *d_atype, const uint8_t *d_fov_ctrl, int32_t *d_loc, int32_t *d_res, int variant,
-                          int pad_h, int pad_w, uint8_t *d_out, int32_t *d_err, void *stream) {
-    const int v = check_fov_args(plan, d_ring, d_head, d_action, d_fov_ctrl, d_loc, d_out);
+                          int pad_h, int pad_w, uint8_t *d_out, int32_t *d_err, void *d_out_norm, int norm_dtype, void *stream) {
+    int v = check_fov_args(plan, d_ring, d_head, d_action, d_fov_ctrl, d_loc, d_out);
     if (v != AGYM_OK) return v;
     if (!d_res || variant < AGYM_OUT_CROP || variant > AGYM_OUT_RESIZE_FULL) return AGYM_ERR_INVALID_ARG;
     if (variant == AGYM_OUT_CROP && (pad_h <= 0 || pad_w <= 0 || pad_w % 4 != 0)) return AGYM_ERR_INVALID_ARG;
+    const agym_config &c = plan->cfg;
+    const size_t bytes = static_cast<size_t>(c.n_envs) * c.frame_stack *
+                         (variant == AGYM_OUT_CROP ? static_cast<size_t>(pad_h) * pad_w : static_cast<size_t>(c.obs_h) * c.obs_w);
+    if ((v = check_norm_args(d_out, bytes, d_out_norm, norm_dtype)) != AGYM_OK) return v;
     return ret(launch_observe_flexible(plan->dev, d_ring, d_head, d_action, d_atype, d_fov_ctrl, d_loc, d_res, variant,
-                                       pad_h, pad_w, d_out, d_err, as_stream(stream)));
+                                       pad_h, pad_w, d_out, d_err, d_out_norm, norm_dtype, as_stream(stream)));
 }
 
 int agym_table_cv2(int n_src, int n_dst, int zero_frac_at_border, int32_t *h_s0, int32_t *h_s1, int32_t *h_coef) {

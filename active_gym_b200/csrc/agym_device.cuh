@@ -17,6 +17,8 @@
 #endif
 
 #include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include <algorithm>
 #include <cstdlib>
@@ -293,6 +295,56 @@ __device__ __forceinline__ void cp_async4_imm(uint32_t smem_addr, const void *gm
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// ---- normalised second output: the reference hands the agent float32(u) / 255
+// (atari_env.py:75, dmc_env.py:183).  The observe kernels can write that value — as f32, or rounded once more to f16 /
+// bf16 — next to the u8 observation, straight from the output words they already hold (no second pass over HBM).
+// norm_u8: the correctly rounded quotient u / 255 by one FMA-corrected step on the reciprocal (q0 = u r, e = u - 255 q0
+// exactly, q = q0 + e r); tests/test_gpu_parity.py compares all 256 values with the IEEE division of k_normalize.
+__device__ __forceinline__ float norm_u8(uint32_t u) {
+    const float x = (float)u, r = 1.0f / 255.0f;
+    const float q0 = x * r;
+    return fmaf(fmaf(-q0, 255.0f, x), r, q0);
+}
+// 4 pixels (one output word) -> dst[index]: 16 bytes of f32, or 8 bytes of f16 / bf16 (dt: AGYM_DTYPE_*)
+__device__ __forceinline__ void norm_store4(int dt, uint32_t word, void *dst, size_t index) {
+    const float f0 = norm_u8(word & 0xffu), f1 = norm_u8((word >> 8) & 0xffu), f2 = norm_u8((word >> 16) & 0xffu), f3 = norm_u8(word >> 24);
+    if (dt == AGYM_DTYPE_F32) {
+        reinterpret_cast<float4 *>(dst)[index] = make_float4(f0, f1, f2, f3);
+    } else if (dt == AGYM_DTYPE_F16) {
+        const __half2 a = __floats2half2_rn(f0, f1), b = __floats2half2_rn(f2, f3);
+        reinterpret_cast<uint2 *>(dst)[index] = make_uint2(*reinterpret_cast<const uint32_t *>(&a), *reinterpret_cast<const uint32_t *>(&b));
+    } else {
+        const __nv_bfloat162 a = __floats2bfloat162_rn(f0, f1), b = __floats2bfloat162_rn(f2, f3);
+        reinterpret_cast<uint2 *>(dst)[index] = make_uint2(*reinterpret_cast<const uint32_t *>(&a), *reinterpret_cast<const uint32_t *>(&b));
+    }
+}
+// 16 pixels (four consecutive output words) -> dst vector `index` (64 bytes of f32, 32 bytes of f16 / bf16)
+__device__ __forceinline__ void norm_store16(int dt, const uint4 v, void *dst, size_t index) {
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    if (dt == AGYM_DTYPE_F32) {
+        float4 *o = reinterpret_cast<float4 *>(dst) + 4 * index;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            o[j] = make_float4(norm_u8(w[j] & 0xffu), norm_u8((w[j] >> 8) & 0xffu), norm_u8((w[j] >> 16) & 0xffu), norm_u8(w[j] >> 24));
+    } else {
+        uint32_t h[8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float f0 = norm_u8(w[j] & 0xffu), f1 = norm_u8((w[j] >> 8) & 0xffu), f2 = norm_u8((w[j] >> 16) & 0xffu), f3 = norm_u8(w[j] >> 24);
+            if (dt == AGYM_DTYPE_F16) {
+                const __half2 a = __floats2half2_rn(f0, f1), b = __floats2half2_rn(f2, f3);
+                h[2 * j] = *reinterpret_cast<const uint32_t *>(&a); h[2 * j + 1] = *reinterpret_cast<const uint32_t *>(&b);
+            } else {
+                const __nv_bfloat162 a = __floats2bfloat162_rn(f0, f1), b = __floats2bfloat162_rn(f2, f3);
+                h[2 * j] = *reinterpret_cast<const uint32_t *>(&a); h[2 * j + 1] = *reinterpret_cast<const uint32_t *>(&b);
+            }
+        }
+        uint4 *o = reinterpret_cast<uint4 *>(dst) + 2 * index;
+        o[0] = make_uint4(h[0], h[1], h[2], h[3]);
+        o[1] = make_uint4(h[4], h[5], h[6], h[7]);
+    }
+}
 
 // ---- packed fp32 pairs (Blackwell FFMA2 / FADD2: two fp32 lanes per issue slot)
 __device__ __forceinline__ uint64_t pack2(float lo, float hi) {

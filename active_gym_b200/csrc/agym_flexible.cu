@@ -577,6 +577,12 @@ __global__ void __launch_bounds__(kFlexThreads + 32, 2) k_observe_flexible_v3(co
             bulk_s2g(out + (size_t)n * tile_bytes, s_tile, (uint32_t)tile_bytes);
             bulk_commit();
         }
+        if (p.norm_out) {   // uniform: the normalised copy of the finished tile; the tile is next written after barrier #1 of
+                            // the following env, which comes after this loop in every thread's program order
+            const uint4 *t4 = reinterpret_cast<const uint4 *>(s_tile);
+            const int nv = tile_bytes >> 4;
+            for (int i = threadIdx.x; i < nv; i += (int)blockDim.x) norm_store16(p.norm_dt, t4[i], p.norm_out, (size_t)n * nv + i);
+        }
     }
     cp_async_wait<0>();
     if (boss) {
@@ -590,10 +596,18 @@ __global__ void __launch_bounds__(kFlexThreads + 32, 2) k_observe_flexible_v3(co
 // --------------------------------------------------------------------------- launchers
 cudaError_t launch_observe_flexible(const DevPlan &p, const uint8_t *ring, const int32_t *head, const double *action,
                                     const int32_t *atype, const uint8_t *ctrl, int32_t *loc, int32_t *res, int variant,
-                                    int pad_h, int pad_w, uint8_t *out, int32_t *err, cudaStream_t st) {
+                                    int pad_h, int pad_w, uint8_t *out, int32_t *err, void *norm_out, int norm_dt,
+                                    cudaStream_t st) {
     cudaError_t e;
     DevPlan q = p;
     q.err = err;
+    q.norm_out = norm_out; q.norm_dt = norm_dt;
+    const size_t out_bytes = (size_t)p.N * p.K * (variant == AGYM_OUT_CROP ? (size_t)pad_h * pad_w : (size_t)p.plane);
+    auto finish = [&](cudaError_t r) {   // kernels without the fused normalised store: a separate pass over the u8 output
+        if (r != cudaSuccess || !norm_out) return r;
+        if (out_bytes % 16 != 0) return cudaErrorInvalidValue;
+        return launch_normalize(out, out_bytes, norm_dt, norm_out, st);
+    };
     if (variant != AGYM_OUT_RESIZE_FULL && p.flexb && p.flexq && !g_disable_std && !g_flex_old) {
         // persistent kernel, 2 CTAs per SM: whatever the fixed buffers leave of ~113 KB goes to t1
         const int oh = variant == AGYM_OUT_CROP ? pad_h : p.S_h, ow = variant == AGYM_OUT_CROP ? pad_w : p.S_w;
@@ -638,7 +652,7 @@ cudaError_t launch_observe_flexible(const DevPlan &p, const uint8_t *ring, const
                 if ((e = set_smem(k_observe_flexible_fast<AGYM_OUT_MASK>, fs)) != cudaSuccess) return e;
                 k_observe_flexible_fast<AGYM_OUT_MASK><<<p.N, kThreads, fs, st>>>(q, ring, head, action, atype, ctrl, loc, res, oh, ow, t1_cap, out);
             }
-            return cudaGetLastError();
+            return finish(cudaGetLastError());
         }
     }
     const size_t smem = sizeof(float) * 2 * (size_t)p.plane;
@@ -649,7 +663,7 @@ cudaError_t launch_observe_flexible(const DevPlan &p, const uint8_t *ring, const
     else if (variant == AGYM_OUT_MASK) { AGYM_LAUNCH_FLEX(AGYM_OUT_MASK) }
     else { AGYM_LAUNCH_FLEX(AGYM_OUT_RESIZE_FULL) }
 #undef AGYM_LAUNCH_FLEX
-    return cudaGetLastError();
+    return finish(cudaGetLastError());
 }
 
 

@@ -46,6 +46,8 @@ struct DevPlan {
     // re-arms it), so a plan must not run agym_observe_flexible on two streams at once
     int32_t *flex_counters;
     int32_t *err;           // per-launch: the caller's device error word (AGYM_ERR_RES_* bits) or null
+    void *norm_out;         // per-launch: normalised second output (same shape as the u8 output) or null
+    int32_t norm_dt;        // its element type, AGYM_DTYPE_*
     const int32_t *pool_i;  // pool base viewed as int32
     int32_t S_max;
     // ---- fast paths (0 = geometry not eligible, use the generic kernels)
@@ -90,14 +92,17 @@ cudaError_t launch_ingest_gray_std(const DevPlan &p, const uint8_t *fa, const ui
 cudaError_t launch_ingest_dmc(const DevPlan &p, const uint8_t *f, const uint8_t *flags, uint8_t *ring,
                               int32_t *head, float *pcache, cudaStream_t st);
 cudaError_t launch_stack(const DevPlan &p, const uint8_t *ring, const int32_t *head, uint8_t *out, cudaStream_t st);
+// norm_out / norm_dt: optional normalised second output of the observe launchers (null = none)
 cudaError_t launch_observe_fixed(const DevPlan &p, const uint8_t *ring, const int32_t *head, const double *action,
-                                 const uint8_t *ctrl, int32_t *loc, int variant, uint8_t *out, cudaStream_t st);
+                                 const uint8_t *ctrl, int32_t *loc, int variant, uint8_t *out, void *norm_out, int norm_dt,
+                                 cudaStream_t st);
 cudaError_t launch_observe_peripheral(const DevPlan &p, const ExpandStd *ew, const uint8_t *ring, const int32_t *head,
                                       const float *pcache, const double *action, const uint8_t *ctrl, int32_t *loc,
-                                      uint8_t *out, cudaStream_t st);
+                                      uint8_t *out, void *norm_out, int norm_dt, cudaStream_t st);
 cudaError_t launch_observe_flexible(const DevPlan &p, const uint8_t *ring, const int32_t *head, const double *action,
                                     const int32_t *atype, const uint8_t *ctrl, int32_t *loc, int32_t *res, int variant,
-                                    int pad_h, int pad_w, uint8_t *out, int32_t *err, cudaStream_t st);
+                                    int pad_h, int pad_w, uint8_t *out, int32_t *err, void *norm_out, int norm_dt,
+                                    cudaStream_t st);
 cudaError_t launch_normalize(const uint8_t *src, size_t n, int dtype, void *dst, cudaStream_t st);
 cudaError_t launch_synth(uint8_t *dst, size_t n, uint64_t seed, cudaStream_t st);
 cudaError_t launch_record_step(int n, int is_reset, const double *raw_reward, const uint8_t *done, const uint8_t *reset_mask,

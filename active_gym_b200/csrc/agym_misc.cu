@@ -9,8 +9,6 @@ namespace {
 // The reference hands the agent float32(u) / 255 (atari_env.py:75, dmc_env.py:183).  Consumer-side
 // convenience: u8 observations -> normalised f32 (bit-identical to the reference's value: IEEE
 // division), f16 or bf16, 16 pixels per thread, 16-byte loads and stores.
-#include <cuda_bf16.h>
-#include <cuda_fp16.h>
 template <int DT>  // 0 f32, 1 f16, 2 bf16
 __global__ void k_normalize(const uint4 *__restrict__ src, void *__restrict__ dst, size_t n_vec) {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n_vec; i += (size_t)gridDim.x * blockDim.x) {

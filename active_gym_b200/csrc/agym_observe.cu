@@ -211,7 +211,9 @@ __global__ void __launch_bounds__(kCropWarps * 32) k_observe_fixed_crop_v2(const
     for (int t = lane; t < words; t += 32) {
         const uint2 o = s_off[t];
         const uint32_t b0 = wb[o.x & 0xffffu], b1 = wb[o.x >> 16], b2 = wb[o.y & 0xffffu], b3 = wb[o.y >> 16];
-        dst[t] = __byte_perm(__byte_perm(b0, b1, 0x0040), __byte_perm(b2, b3, 0x0040), 0x5410);
+        const uint32_t word = __byte_perm(__byte_perm(b0, b1, 0x0040), __byte_perm(b2, b3, 0x0040), 0x5410);
+        dst[t] = word;
+        if (p.norm_out) norm_store4(p.norm_dt, word, p.norm_out, (size_t)n * words + t);   // uniform branch
     }
 }
 
@@ -694,6 +696,12 @@ __global__ void __launch_bounds__(((StdGeom::Q * StdGeom::SEG * K + 31) / 32) * 
             bulk_s2g(out + (size_t)e * (K * PLANE_W * 4), tile, K * PLANE_W * 4);
             bulk_commit();
         }
+        if (p.norm_out) {   // uniform: the normalised copy of the same tile, 16 pixels per thread and pass; the tile is not
+                            // written again before the barrier of the NEXT iteration, which follows this loop in program order
+            const uint4 *t4 = reinterpret_cast<const uint4 *>(tile);
+            for (int i = tid; i < K * PLANE_W / 4; i += (int)blockDim.x)
+                norm_store16(p.norm_dt, t4[i], p.norm_out, (size_t)e * (K * PLANE_W / 4) + i);
+        }
     }
     if (tid == 0) bulk_wait_read<0>();  // shared memory must outlive the last store's reads
 }
@@ -702,8 +710,21 @@ __global__ void __launch_bounds__(((StdGeom::Q * StdGeom::SEG * K + 31) / 32) * 
 }  // namespace
 
 // --------------------------------------------------------------------------- launchers
-cudaError_t launch_observe_fixed(const DevPlan &p, const uint8_t *ring, const int32_t *head, const double *action,
-                                 const uint8_t *ctrl, int32_t *loc, int variant, uint8_t *out, cudaStream_t st) {
+namespace {
+// the normalised second output as a separate pass over the u8 output (kernels without the fused store)
+cudaError_t normalize_after(cudaError_t e, const uint8_t *out, size_t bytes, void *norm_out, int norm_dt, cudaStream_t st) {
+    if (e != cudaSuccess || !norm_out) return e;
+    if (bytes % 16 != 0) return cudaErrorInvalidValue;   // the separate pass converts 16 pixels per thread
+    return launch_normalize(out, bytes, norm_dt, norm_out, st);
+}
+}  // namespace
+
+cudaError_t launch_observe_fixed(const DevPlan &p0, const uint8_t *ring, const int32_t *head, const double *action,
+                                 const uint8_t *ctrl, int32_t *loc, int variant, uint8_t *out, void *norm_out, int norm_dt,
+                                 cudaStream_t st) {
+    DevPlan p = p0;
+    p.norm_out = norm_out; p.norm_dt = norm_dt;
+    const size_t out_bytes = (size_t)p.N * p.K * (variant == AGYM_OUT_CROP ? p.f_h * p.f_w : p.plane);
     cudaError_t e;
     const int crop_nwx = (p.f_w + 2) / 4 + 1;  // aligned words that cover f_w bytes at any byte offset
     const size_t crop_smem = a16((size_t)(p.K * p.f_h * p.f_w / 4) * 8) + (size_t)kCropWarps * p.K * p.f_h * crop_nwx * 4;
@@ -711,6 +732,7 @@ cudaError_t launch_observe_fixed(const DevPlan &p, const uint8_t *ring, const in
         crop_smem <= 64 * 1024 && p.K * p.f_h * crop_nwx * 4 + 4 < 65536) {
         if ((e = set_smem(k_observe_fixed_crop_v2, crop_smem)) != cudaSuccess) return e;
         k_observe_fixed_crop_v2<<<(p.N + kCropWarps - 1) / kCropWarps, kCropWarps * 32, crop_smem, st>>>(p, ring, head, action, ctrl, loc, out, crop_nwx);
+        return cudaGetLastError();   // the normalised output, if any, was written by the kernel
     } else if (variant == AGYM_OUT_CROP && (p.K * p.f_h * p.f_w) % 4 == 0 && !g_disable_std) {
         k_observe_fixed_crop_warp<<<(p.N + kThreads / 32 - 1) / (kThreads / 32), kThreads, 0, st>>>(p, ring, head, action, ctrl, loc, out);
     } else if (variant == AGYM_OUT_CROP) {
@@ -722,12 +744,15 @@ cudaError_t launch_observe_fixed(const DevPlan &p, const uint8_t *ring, const in
         if ((e = set_smem(k_observe_fixed<AGYM_OUT_RESIZE_FULL>, smem)) != cudaSuccess) return e;
         k_observe_fixed<AGYM_OUT_RESIZE_FULL><<<p.N, kThreads, smem, st>>>(p, ring, head, action, ctrl, loc, out);
     }
-    return cudaGetLastError();
+    return normalize_after(cudaGetLastError(), out, out_bytes, norm_out, norm_dt, st);
 }
 
-cudaError_t launch_observe_peripheral(const DevPlan &p, const ExpandStd *ew, const uint8_t *ring, const int32_t *head,
+cudaError_t launch_observe_peripheral(const DevPlan &p0, const ExpandStd *ew, const uint8_t *ring, const int32_t *head,
                                       const float *pcache, const double *action, const uint8_t *ctrl, int32_t *loc,
-                                      uint8_t *out, cudaStream_t st) {
+                                      uint8_t *out, void *norm_out, int norm_dt, cudaStream_t st) {
+    DevPlan p = p0;
+    p.norm_out = norm_out; p.norm_dt = norm_dt;
+    const size_t out_bytes = (size_t)p.N * p.K * p.plane;
     const size_t smem = a16(p.plane) + sizeof(float) * ((size_t)p.S_h * p.p_w + (size_t)p.p_h * p.p_w + (size_t)p.p_h * p.S_w);
     cudaError_t e;
     const int quads = p.S_w / 4;
@@ -791,7 +816,7 @@ cudaError_t launch_observe_peripheral(const DevPlan &p, const ExpandStd *ew, con
         else if (p.K % 2 == 0) AGYM_LAUNCH_PF(2, 0)
         else AGYM_LAUNCH_PF(1, 0)
 #undef AGYM_LAUNCH_PF
-        return cudaGetLastError();
+        return normalize_after(cudaGetLastError(), out, out_bytes, norm_out, norm_dt, st);
     }
     if (pcache) {
         if ((e = set_smem(k_observe_peripheral<true>, smem)) != cudaSuccess) return e;
@@ -800,7 +825,7 @@ cudaError_t launch_observe_peripheral(const DevPlan &p, const ExpandStd *ew, con
         if ((e = set_smem(k_observe_peripheral<false>, smem)) != cudaSuccess) return e;
         k_observe_peripheral<false><<<p.N, kThreads, smem, st>>>(p, ring, head, pcache, action, ctrl, loc, out);
     }
-    return cudaGetLastError();
+    return normalize_after(cudaGetLastError(), out, out_bytes, norm_out, norm_dt, st);
 }
 
 

@@ -204,33 +204,48 @@ class ObservationPath:
             return self._ctrl_reset
         return self._dev_u8(ctrl, (self.n_envs,))
 
-    def observe_fixed(self, action, variant: str = "crop", ctrl=None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """FixedFovealEnv._fov_step + _get_fov_state (fov_env.py:166-203)."""
+    def _norm(self, out: torch.Tensor, norm_out: Optional[torch.Tensor]):
+        """(pointer, AGYM_DTYPE_*) of the optional normalised second output: a contiguous f32 / f16 / bf16 tensor of
+        ``out``'s shape that receives float32(u) / 255 (atari_env.py:75) in the same launch."""
+        if norm_out is None:
+            return None, 0
+        if norm_out.shape != out.shape or norm_out.device != self.device or not norm_out.is_contiguous() \
+                or norm_out.dtype not in self._NORM_DTYPES:
+            raise TypeError("norm_out must be a contiguous float32 / float16 / bfloat16 tensor of the observation's shape on the path's device")
+        return norm_out.data_ptr(), self._NORM_DTYPES[norm_out.dtype]
+
+    def observe_fixed(self, action, variant: str = "crop", ctrl=None, out: Optional[torch.Tensor] = None,
+                      norm_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """FixedFovealEnv._fov_step + _get_fov_state (fov_env.py:166-203).  ``norm_out``: see ``_norm``."""
         ctrl_t = self._ctrl(ctrl)
         act = None if action is None else self._dev_action(action)
         if out is None:
             out = torch.empty(self.out_shape("fixed", variant), dtype=torch.uint8, device=self.device)
+        np_, nd = self._norm(out, norm_out)
         with torch.cuda.device(self.device):
             _lib.check(self._L.agym_observe_fixed(self._plan, _ptr(self.ring), _ptr(self.head), _ptr(act), _ptr(ctrl_t),
-                                                  _ptr(self.loc), VARIANTS[variant], _ptr(out), self._stream()),
+                                                  _ptr(self.loc), VARIANTS[variant], _ptr(out), np_, nd, self._stream()),
                        "agym_observe_fixed")
         return out
 
-    def observe_peripheral(self, action, ctrl=None, out: Optional[torch.Tensor] = None, use_cache: bool = True) -> torch.Tensor:
+    def observe_peripheral(self, action, ctrl=None, out: Optional[torch.Tensor] = None, use_cache: bool = True,
+                           norm_out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """FixedFovealPeripheralEnv._get_fov_state (fov_env.py:375-388), loc update fused."""
         ctrl_t = self._ctrl(ctrl)
         act = None if action is None else self._dev_action(action)
         if out is None:
             out = torch.empty(self.out_shape("peripheral", "mask"), dtype=torch.uint8, device=self.device)
         pc = self.pcache if use_cache else None
+        np_, nd = self._norm(out, norm_out)
         with torch.cuda.device(self.device):
             _lib.check(self._L.agym_observe_peripheral(self._plan, _ptr(self.ring), _ptr(self.head), _ptr(pc), _ptr(act),
-                                                       _ptr(ctrl_t), _ptr(self.loc), _ptr(out), self._stream()),
+                                                       _ptr(ctrl_t), _ptr(self.loc), _ptr(out), np_, nd, self._stream()),
                        "agym_observe_peripheral")
         return out
 
     def observe_flexible(self, action, action_type=None, variant: str = "mask", ctrl=None,
-                         pad: Optional[Tuple[int, int]] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                         pad: Optional[Tuple[int, int]] = None, out: Optional[torch.Tensor] = None,
+                         norm_out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """FlexibleFovealEnv._fov_step + _get_fov_state (fov_env.py:270-330)."""
         ctrl_t = self._ctrl(ctrl)
         act = None if action is None else self._dev_action(action)
@@ -241,10 +256,11 @@ class ObservationPath:
         pad = tuple(pad) if pad is not None else self.obs_size
         if out is None:
             out = torch.empty(self.out_shape("flexible", variant, pad), dtype=torch.uint8, device=self.device)
+        np_, nd = self._norm(out, norm_out)
         with torch.cuda.device(self.device):
             _lib.check(self._L.agym_observe_flexible(self._plan, _ptr(self.ring), _ptr(self.head), _ptr(act), _ptr(at),
                                                      _ptr(ctrl_t), _ptr(self.loc), _ptr(self.res), VARIANTS[variant],
-                                                     int(pad[0]), int(pad[1]), _ptr(out), _ptr(self.err), self._stream()),
+                                                     int(pad[0]), int(pad[1]), _ptr(out), _ptr(self.err), np_, nd, self._stream()),
                        "agym_observe_flexible")
         return out
 

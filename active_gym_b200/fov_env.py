@@ -191,6 +191,13 @@ class FixedFovealEnv(Wrapper):
         self._rec = self.env if isinstance(self.env, RecordWrapper) else None
         self._obs = None
         self._host = None
+        # args.obs_dtype = torch.float16 / bfloat16 / float32: observations come back NORMALISED, float32(u8) / 255
+        # (what the reference returns, atari_env.py:75), written by the observe kernel as a second output next to the
+        # u8 tensor (kept in `last_obs_u8`).  Device observations only.
+        self.obs_dtype = getattr(args, "obs_dtype", None)
+        if self.obs_dtype is not None and self.host_obs:
+            raise ValueError("obs_dtype (normalised device observations) and host_obs (pinned u8 host observations) exclude each other")
+        self.last_obs_u8 = None
 
     # ---- state the reference exposes as attributes
     @property
@@ -201,13 +208,22 @@ class FixedFovealEnv(Wrapper):
     def variant(self) -> str:
         return "mask" if self.mask_out else ("resize_full" if self.resize else "crop")
 
-    def _observe(self, action, ctrl, action_type=None):
-        return self.path.observe_fixed(action, variant=self.variant, ctrl=ctrl, host_out=self.host_obs)
+    def _norm_buffer(self):
+        if self.obs_dtype is None:
+            return None
+        kind = "peripheral" if self._kind == "peripheral" else self._kind
+        return torch.empty(self.path.out_shape(kind, self.variant), dtype=self.obs_dtype, device=self.path.device)
+
+    def _observe(self, action, ctrl, action_type=None, norm_out=None):
+        return self.path.observe_fixed(action, variant=self.variant, ctrl=ctrl, host_out=self.host_obs, norm_out=norm_out)
 
     def _run_observe(self, action, ctrl, action_type=None):
-        r = self._observe(action, ctrl, action_type)
+        norm = self._norm_buffer()
+        r = self._observe(action, ctrl, action_type, norm_out=norm) if norm is not None else self._observe(action, ctrl, action_type)
         if self.host_obs:
             self._obs, self._host = r
+        elif norm is not None:
+            self.last_obs_u8, self._obs, self._host = r, norm, None
         else:
             self._obs, self._host = r, None
 
@@ -308,10 +324,11 @@ class FlexibleFovealEnv(FixedFovealEnv):
             if (r < 1).any() or (r > np.array(self.obs_size)).any() or (r != np.floor(r)).any():
                 raise ValueError("FOV_RES actions must be integer window sizes within [1, obs_size]")
 
-    def _observe(self, action, ctrl, action_type=None):
+    def _observe(self, action, ctrl, action_type=None, norm_out=None):
         self._check_res(action, action_type)
         self._device_actions = isinstance(action, torch.Tensor) and action.device.type == "cuda"
-        return self.path.observe_flexible(action, action_type, variant=self.variant, ctrl=ctrl, host_out=self.host_obs)
+        return self.path.observe_flexible(action, action_type, variant=self.variant, ctrl=ctrl, host_out=self.host_obs,
+                                          norm_out=norm_out)
 
     def _raise_device_errors(self):
         """FOV_RES actions given as device tensors cannot be validated before the launch; the kernels report what they
@@ -351,8 +368,8 @@ class FixedFovealPeripheralEnv(FixedFovealEnv):
         if self.path.peripheral_res != self.peripheral_res:
             raise ValueError("the base env was built from different args (peripheral_res mismatch)")
 
-    def _observe(self, action, ctrl, action_type=None):
-        return self.path.observe_peripheral(action, ctrl=ctrl, host_out=self.host_obs)
+    def _observe(self, action, ctrl, action_type=None, norm_out=None):
+        return self.path.observe_peripheral(action, ctrl=ctrl, host_out=self.host_obs, norm_out=norm_out)
 
 
 class SingleEnvAdapter:

@@ -343,8 +343,10 @@ class PipelinedPath:
         self.join()
         return out
 
-    def _observe(self, kind: str, action, action_type, variant: str, ctrl, pad, out, host_out: bool):
+    def _observe(self, kind: str, action, action_type, variant: str, ctrl, pad, out, host_out: bool, norm_out=None):
         shape = self.out_shape(kind, variant, pad)
+        if norm_out is not None and tuple(norm_out.shape) != tuple(shape):
+            raise ValueError(f"norm_out must have the observation's shape {tuple(shape)}")
         if out is None and host_out:   # shard streams keep writing it after this call returns: never hand it to the allocator
             ok = (kind, variant, tuple(shape))
             if ok not in self._d_out:
@@ -370,12 +372,13 @@ class PipelinedPath:
         for i, lo, hi in self._shards():
             p, a = self.paths[i], None if act is None else act[i]
             c = None if ct is None else ct[i]
+            nrm = None if norm_out is None else norm_out[lo:hi]
             if kind == "peripheral":
-                p.observe_peripheral(a, ctrl=c, out=out[lo:hi])
+                p.observe_peripheral(a, ctrl=c, out=out[lo:hi], norm_out=nrm)
             elif kind == "flexible":
-                p.observe_flexible(a, None if at is None else at[i], variant=variant, ctrl=c, pad=pad, out=out[lo:hi])
+                p.observe_flexible(a, None if at is None else at[i], variant=variant, ctrl=c, pad=pad, out=out[lo:hi], norm_out=nrm)
             else:
-                p.observe_fixed(a, variant=variant, ctrl=c, out=out[lo:hi])
+                p.observe_fixed(a, variant=variant, ctrl=c, out=out[lo:hi], norm_out=nrm)
             if host_out:
                 h_obs[lo:hi].copy_(out[lo:hi], non_blocking=True)
                 h_loc[lo:hi].copy_(self.loc[lo:hi], non_blocking=True)
@@ -388,23 +391,23 @@ class PipelinedPath:
         self.join()
         return out
 
-    def observe_fixed(self, action, variant: str = "crop", ctrl=None, out=None, host_out: bool = False):
+    def observe_fixed(self, action, variant: str = "crop", ctrl=None, out=None, host_out: bool = False, norm_out=None):
         """FixedFovealEnv._fov_step + _get_fov_state (fov_env.py:166-203).  ``host_out``: also copy the
         observations and fov_loc to pinned host memory on the shard streams; returns (out, (h_obs, h_loc, None)),
         valid after ``sync()``."""
-        return self._observe("fixed", action, None, variant, ctrl, None, out, host_out)
+        return self._observe("fixed", action, None, variant, ctrl, None, out, host_out, norm_out)
 
-    def observe_peripheral(self, action, ctrl=None, out=None, use_cache: bool = True, host_out: bool = False):
+    def observe_peripheral(self, action, ctrl=None, out=None, use_cache: bool = True, host_out: bool = False, norm_out=None):
         """FixedFovealPeripheralEnv._get_fov_state (fov_env.py:375-388), loc update fused."""
         if not use_cache:
             raise ValueError("the sharded path always uses the cached squeeze (build with cache_peripheral=False to drop it)")
-        return self._observe("peripheral", action, None, "mask", ctrl, None, out, host_out)
+        return self._observe("peripheral", action, None, "mask", ctrl, None, out, host_out, norm_out)
 
     def observe_flexible(self, action, action_type=None, variant: str = "mask", ctrl=None, pad=None, out=None,
-                         host_out: bool = False):
+                         host_out: bool = False, norm_out=None):
         """FlexibleFovealEnv._fov_step + _get_fov_state (fov_env.py:270-330)."""
         pad = tuple(pad) if pad is not None else self.obs_size
-        return self._observe("flexible", action, action_type, variant, ctrl, pad, out, host_out)
+        return self._observe("flexible", action, action_type, variant, ctrl, pad, out, host_out, norm_out)
 
     def record_step(self, raw_reward=None, done=None, reset_mask=None, is_reset: bool = False,
                     trace_row: Optional[torch.Tensor] = None, with_res: bool = False, host_out: bool = False):

@@ -40,6 +40,26 @@ if ROOT not in sys.path:
 # (measured: the same pipeline 18.8 ms / step on fresh streams, 22-25 ms once more than 8 streams had been created).
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
+_STDOUT_FD = None
+
+
+def quiet_stdout():
+    """Rank 0 prints ONE JSON line on stdout.  Libraries write there too (NCCL's version banner under NCCL_DEBUG=VERSION,
+    which this image sets): from here on file descriptor 1 is stderr, and `emit` writes the line to the real stdout."""
+    global _STDOUT_FD
+    if _STDOUT_FD is None:
+        sys.stdout.flush()
+        _STDOUT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _STDOUT_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_STDOUT_FD, data)
+
 import numpy as np  # noqa: E402
 
 METRIC, UNIT = "foveal_obs_per_sec", "obs/s"
@@ -299,7 +319,7 @@ def run_reference_arm(a):
                          "sample": f"{procs} procs x {per_step} env-steps per bench step of {what}"},
         "e2e": {"value": total, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------ clocks
@@ -784,7 +804,7 @@ def run_b200_arm(a):
             "collectives": "none on the data path; NCCL is initialised only for this benchmark's barrier and the max-over-ranks of the time",
             "sources_sha16": sources_hash(),
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
@@ -807,6 +827,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "b200" else a.warmup
+    quiet_stdout()
     if a.impl == "reference":
         run_reference_arm(a)
     else:

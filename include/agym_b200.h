@@ -78,6 +78,11 @@ typedef enum agym_status {
 #define AGYM_ERR_RES_RANGE 1     /* a FOV_RES action outside [1, obs_size] (or NaN) was clamped   */
 #define AGYM_ERR_RES_FRACTION 2  /* a FOV_RES action with a fractional part was truncated         */
 
+/* element type of the normalised outputs (agym_normalize, d_out_norm of the observe calls) */
+#define AGYM_DTYPE_F32 0
+#define AGYM_DTYPE_F16 1
+#define AGYM_DTYPE_BF16 2
+
 /* sensory_action_type of the flexible fovea (fov_env.py:236-238) */
 #define AGYM_ATYPE_FOV_LOC 0
 #define AGYM_ATYPE_FOV_RES 1
@@ -139,19 +144,26 @@ AGYM_API int agym_ingest_dmc(const agym_plan *plan, const uint8_t *d_frames, con
 AGYM_API int agym_stack(const agym_plan *plan, const uint8_t *d_ring, const int32_t *d_head, uint8_t *d_out,
                void *stream);
 
-/* Replaces FixedFovealEnv._fov_step + _get_fov_state (fov_env.py:166-203): updates d_loc
+/* Normalised second output of the three observe calls: d_out_norm (may be NULL) receives,
+ * in the layout of d_out, the value the reference hands to the agent — float32(u) / 255 (atari_env.py:75,
+ * dmc_env.py:183) — as norm_dtype AGYM_DTYPE_F32 (bit-identical to the reference's float32) or rounded once more to
+ * F16 / BF16.  The kernels of the standard geometries write it from the output tile they hold in shared memory / the
+ * output words they hold in registers (no second pass over HBM); other geometries run agym_normalize on d_out behind
+ * the observe kernel.  Both outputs must be 16-byte aligned and a multiple of 16 pixels long.
+ *
+ * Replaces FixedFovealEnv._fov_step + _get_fov_state (fov_env.py:166-203): updates d_loc
  * from the sensory action (f64 [N][2]; may be NULL when every env is RESET/KEEP) and writes
  * the observation.  d_out: u8 [N][K][f_h][f_w] (CROP) or [N][K][S_h][S_w] (MASK, RESIZE_FULL). */
 AGYM_API int agym_observe_fixed(const agym_plan *plan, const uint8_t *d_ring, const int32_t *d_head,
                        const double *d_action, const uint8_t *d_fov_ctrl, int32_t *d_loc,
-                       int variant, uint8_t *d_out, void *stream);
+                       int variant, uint8_t *d_out, void *d_out_norm, int norm_dtype, void *stream);
 
 /* Replaces FixedFovealPeripheralEnv._get_fov_state (fov_env.py:375-388) with the loc update
  * fused in.  d_pcache may be NULL (the squeeze is then recomputed from the ring).
  * d_out: u8 [N][K][S_h][S_w]. */
 AGYM_API int agym_observe_peripheral(const agym_plan *plan, const uint8_t *d_ring, const int32_t *d_head,
                             const float *d_pcache, const double *d_action, const uint8_t *d_fov_ctrl,
-                            int32_t *d_loc, uint8_t *d_out, void *stream);
+                            int32_t *d_loc, uint8_t *d_out, void *d_out_norm, int norm_dtype, void *stream);
 
 /* Replaces FlexibleFovealEnv._fov_step + _get_fov_state (fov_env.py:270-330).
  * d_atype: i32 [N] (NULL = all FOV_LOC).  CROP writes the variable-size patch into the
@@ -163,7 +175,7 @@ AGYM_API int agym_observe_peripheral(const agym_plan *plan, const uint8_t *d_rin
 AGYM_API int agym_observe_flexible(const agym_plan *plan, const uint8_t *d_ring, const int32_t *d_head,
                           const double *d_action, const int32_t *d_atype, const uint8_t *d_fov_ctrl,
                           int32_t *d_loc, int32_t *d_res, int variant, int pad_h, int pad_w,
-                          uint8_t *d_out, int32_t *d_err, void *stream);
+                          uint8_t *d_out, int32_t *d_err, void *d_out_norm, int norm_dtype, void *stream);
 
 /* Replaces RecordWrapper's episode counters (fov_env.py:15-67) and the fov_loc / fov_res trace that
  * save_transition keeps when record=True (fov_env.py:152-154, 205-207, 253-256, 332-335), for N envs on the device.
@@ -192,12 +204,9 @@ AGYM_API int agym_table_blur(int r, int f, int32_t *h_xmin, float *h_w, uint16_t
                              int32_t *halves);
 
 /* Consumer-side convenience: u8 observations -> the reference's normalised value
- * float32(u) / 255 (atari_env.py:75, dmc_env.py:183).  AGYM_DTYPE_F32 is bit-identical to the reference's
- * float32; F16 / BF16 round that value once more.  n_bytes: number of pixels, a multiple of 16; both
- * pointers 16-byte aligned. */
-#define AGYM_DTYPE_F32 0
-#define AGYM_DTYPE_F16 1
-#define AGYM_DTYPE_BF16 2
+ * float32(u) / 255 (atari_env.py:75, dmc_env.py:183) as a pass of its own.  AGYM_DTYPE_F32 is bit-identical to the
+ * reference's float32; F16 / BF16 round that value once more.  n_bytes: number of pixels, a multiple of 16; both
+ * pointers 16-byte aligned.  (The observe calls can write the same values as a second output, see above.) */
 AGYM_API int agym_normalize(const uint8_t *d_src, size_t n_bytes, int dtype, void *d_dst, void *stream);
 
 /* Benchmark / test helper: fills d_dst with a counter-based hash of (seed, byte index). */

@@ -139,27 +139,29 @@ class OraclePath:
         loc[reset] = self.init_loc
         res[reset] = np.array(self.fov_size, np.int32)
 
-    def _finish(self, out, host_out, flexible=False):
+    def _finish(self, out, host_out, flexible=False, norm_out=None):
         out = torch.from_numpy(np.clip(np.rint(out), 0, 255).astype(np.uint8)) if out.dtype != np.uint8 else torch.from_numpy(out)
+        if norm_out is not None:   # float32(u) / 255, rounded once more for f16 / bf16 (atari_env.py:75)
+            norm_out.copy_((out.to(torch.float32) / 255.0).to(norm_out.dtype))
         if host_out:
             return out, (out, self.loc.clone(), self.res.clone() if flexible else None)
         return out
 
-    def observe_fixed(self, action, variant="crop", ctrl=None, out=None, host_out=False):
+    def observe_fixed(self, action, variant="crop", ctrl=None, out=None, host_out=False, norm_out=None):
         self._update(action, None, ctrl, False)
         o = orc.observe_fixed(self._ring, self._head, self.loc.numpy(), self.fov_size, variant)
-        return self._finish(o, host_out)
+        return self._finish(o, host_out, norm_out=norm_out)
 
-    def observe_peripheral(self, action, ctrl=None, out=None, use_cache=True, host_out=False):
+    def observe_peripheral(self, action, ctrl=None, out=None, use_cache=True, host_out=False, norm_out=None):
         self._update(action, None, ctrl, False)
         o = orc.observe_peripheral(self._ring, self._head, self.loc.numpy(), self.fov_size, self.peripheral_res)
-        return self._finish(o, host_out)
+        return self._finish(o, host_out, norm_out=norm_out)
 
-    def observe_flexible(self, action, action_type=None, variant="mask", ctrl=None, pad=None, out=None, host_out=False):
+    def observe_flexible(self, action, action_type=None, variant="mask", ctrl=None, pad=None, out=None, host_out=False, norm_out=None):
         self._update(action, action_type, ctrl, True)
         o = orc.observe_flexible(self._ring, self._head, self.loc.numpy(), self.res.numpy(), self.fov_size, variant,
                                  pad=pad if pad is not None else self.obs_size)
-        return self._finish(o, host_out, flexible=True)
+        return self._finish(o, host_out, flexible=True, norm_out=norm_out)
 
     # ---- RecordWrapper counters (restates k_record_step)
     def record_step(self, raw_reward=None, done=None, reset_mask=None, is_reset=False, trace_row=None, with_res=False,

@@ -223,3 +223,43 @@ def test_normalize_is_the_reference_float32_value():
     assert torch.equal(p.normalize(u, torch.bfloat16).cpu(), torch.from_numpy(want).to(torch.bfloat16))
     allv = torch.arange(256, dtype=torch.uint8).repeat(2).cuda()  # every value
     assert np.array_equal(_np(p.normalize(allv))[:256], np.arange(256, dtype=np.float32) / np.float32(255.0))
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.bfloat16])
+def test_normalised_second_output_of_the_observe_kernels_is_bit_identical_to_normalize(dtype):
+    """the observe kernels write float32(u) / 255 (atari_env.py:75) as a second output from the tile /
+    words they hold — the standard-geometry kernels in the same launch (peripheral_std, flexible_v3, crop_v2), the
+    table-driven ones through a normalise pass behind them — bit-identical to agym_normalize of the u8 output."""
+    rng = np.random.default_rng(8)
+    n, K = 333, 4
+    p = _path(n, K, fov_size=(30, 30), peripheral_res=(20, 20), sensory_action_mode="absolute")
+    for step in range(K + 1):
+        fa = rng.integers(0, 256, (n, 210, 160), dtype=np.uint8)
+        p.ingest_atari(fa, fa, np.full(n, 5 if step == 0 else 3, np.uint8))
+    a = rng.integers(0, 55, (n, 2)).astype(np.float64)
+    at = rng.integers(0, 2, n).astype(np.int32)
+    af = np.where(at[:, None] == 1, rng.integers(20, 51, (n, 2)), a).astype(np.float64)
+    cases = [
+        ("peripheral", lambda no: p.observe_peripheral(a, norm_out=no)),
+        ("peripheral uncached (generic kernel + pass)", lambda no: p.observe_peripheral(a, use_cache=False, norm_out=no)),
+        ("crop", lambda no: p.observe_fixed(a, variant="crop", norm_out=no)),
+        ("mask (generic kernel + pass)", lambda no: p.observe_fixed(a, variant="mask", norm_out=no)),
+        ("flexible mask", lambda no: p.observe_flexible(af, at, variant="mask", norm_out=no)),
+        ("flexible crop", lambda no: p.observe_flexible(af, at, variant="crop", pad=(84, 84), norm_out=no)),
+        ("flexible resize_full (generic kernel + pass)", lambda no: p.observe_flexible(af, at, variant="resize_full", norm_out=no)),
+    ]
+    for name, call in cases:
+        shape = call(None).shape
+        no = torch.full(shape, -1.0, dtype=dtype, device="cuda")
+        out = call(no)
+        want = p.normalize(out, dtype)
+        assert torch.equal(no.view(torch.int16 if dtype != torch.float32 else torch.int32),
+                           want.view(torch.int16 if dtype != torch.float32 else torch.int32)), name
+    # every u8 value: the FMA-corrected quotient of the fused stores == the IEEE division, bit for bit
+    q = _path(64, 4, fov_size=(30, 30))
+    q.ring.copy_(torch.arange(64 * 4 * 7056, device="cuda").remainder(256).to(torch.uint8).view(64, 4, 84, 84))
+    no = torch.empty((64, 4, 30, 30), dtype=torch.float32, device="cuda")
+    out = q.observe_fixed(np.zeros((64, 2)), variant="crop", norm_out=no)
+    ref = out.cpu().numpy().astype(np.float32) / np.float32(255.0)
+    assert set(np.unique(out.cpu().numpy()).tolist()) == set(range(256))
+    assert np.array_equal(no.cpu().numpy().view(np.uint32), ref.view(np.uint32))

@@ -94,3 +94,21 @@ def test_sharded_vec_env_equals_one_batch(backend, monkeypatch):
                            else torch.as_tensor(i_sh["fov_loc"]), torch.as_tensor(i_one["fov_loc"])), step
         assert r.shape == (n,) and d.shape == (n,)
     sh.close()
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_env_returns_normalised_observations_when_obs_dtype_is_set(backend, monkeypatch):
+    """args.obs_dtype: the env hands out float32(u8) / 255 (the reference's values, atari_env.py:75) in the requested
+    float type, the u8 tensor stays available in last_obs_u8."""
+    import active_gym_b200 as ag
+    from active_gym_b200.sources import PinnedFrameSource
+    _backend(monkeypatch, backend)
+    n = 6
+    for make, kw in ((ag.AtariFixedFovealPeripheralEnv, {}), (ag.AtariFixedFovealEnv, {}), (ag.AtariFlexibleFovealEnv, dict(mask_out=True))):
+        env = make(_args(obs_dtype=torch.float16, **kw), num_envs=n, source=PinnedFrameSource(n, pool=3))
+        obs, _ = env.reset()
+        act = {"motor_action": np.zeros(n, np.int64), "sensory_action": np.full((n, 2), 3.0), "sensory_action_type": np.zeros(n, np.int64)}
+        obs, *_ = env.step(act)
+        assert obs.dtype == torch.float16 and obs.shape == env.last_obs_u8.shape
+        want = (env.last_obs_u8.to(torch.float32) / 255.0).to(torch.float16)
+        assert torch.equal(obs.cpu(), want.cpu())

@@ -1,20 +1,42 @@
 #!/usr/bin/env python
-"""End-to-end (host buffers in / out) sweep on one GPU: env-API pipeline at several shard counts next to the pure-copy
+"""End-to-end (host buffers in / out) probe: the env-API pipeline at several shard counts next to the pure-copy
 ceiling of the same byte volumes (pinned H2D of the packed raw rows, pinned D2H of the observations, both at once).
-usage: e2e_sweep.py [workload] [steps]   -> JSON lines"""
+Under torchrun every rank runs the same phase at the same time (barrier before each), so the numbers show what the
+host's memory system delivers to N GPUs together.
+usage: [torchrun --nproc-per-node N] e2e_sweep.py [workload] [steps] [shards,shards,...]   -> JSON lines (rank 0)"""
 import json, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import bench  # sets CUDA_DEVICE_MAX_CONNECTIONS before the CUDA context exists
 import numpy as np
 import torch
-import bench
 
 wname = sys.argv[1] if len(sys.argv) > 1 else "atari_peripheral"
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 8
+shard_list = [int(v) for v in sys.argv[3].split(",")] if len(sys.argv) > 3 else [1, 2, 4]
 w = bench.WORKLOADS[wname]
 n = w["n"]
-dev = torch.device("cuda:0")
+rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+dev = torch.device(f"cuda:{local}")
 torch.cuda.set_device(dev)
-rank = int(os.environ.get("RANK", "0"))
+dist = None
+if world > 1:
+    import torch.distributed as dist
+    dist.init_process_group("nccl", device_id=dev)
+
+
+def barrier():
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def gather(obj):
+    if dist is None:
+        return [obj]
+    out = [None] * world
+    dist.all_gather_object(out, obj)
+    return out
 
 
 def copy_ceiling(n_streams):
@@ -38,18 +60,32 @@ def copy_ceiling(n_streams):
                         d_in[lo_i:hi_i].copy_(h_in[lo_i:hi_i], non_blocking=True)
                     if mode in ("d2h", "both"):
                         h_out[lo_o:hi_o].copy_(d_out[lo_o:hi_o], non_blocking=True)
-        go(); torch.cuda.synchronize()
+        go()
+        barrier()
         t0 = time.perf_counter()
         for _ in range(steps):
             go()
         torch.cuda.synchronize()
         dt = (time.perf_counter() - t0) / steps
-        res[mode] = {"ms": dt * 1e3, "gbs_in": n * per_env_in / dt / 1e9 if mode != "d2h" else 0, "gbs_out": n * per_env_out / dt / 1e9 if mode != "h2d" else 0}
+        res[mode] = {"ms": round(dt * 1e3, 3), "gbs_in": round(n * per_env_in / dt / 1e9, 2) if mode != "d2h" else 0,
+                     "gbs_out": round(n * per_env_out / dt / 1e9, 2) if mode != "h2d" else 0}
     return res
 
 
-print(json.dumps({"rank": rank, "workload": wname, "copy_ceiling_8_streams": copy_ceiling(8), "copy_ceiling_2_streams": copy_ceiling(2)}), flush=True)
-for shards in (1, 2, 3, 4):
+c = gather(copy_ceiling(2))
+if rank == 0:
+    agg = {m: {"ms_max": max(r[m]["ms"] for r in c), "gbs_in_sum": round(sum(r[m]["gbs_in"] for r in c), 1),
+               "gbs_out_sum": round(sum(r[m]["gbs_out"] for r in c), 1)} for m in ("h2d", "d2h", "both")}
+    print(json.dumps({"n_gpus": world, "workload": wname, "envs_per_gpu": n, "copy_ceiling": agg, "per_rank": c}), flush=True)
+for shards in shard_list:
+    barrier()
     dt, h2d, d2h = bench.measure_e2e(torch, wname, n, dev, steps, 2, shards)
-    print(json.dumps({"rank": rank, "workload": wname, "shards": shards, "ms_per_step": dt / steps * 1e3, "obs_per_s": n * steps / dt,
-                      "h2d_mb": h2d / 1e6, "d2h_mb": d2h / 1e6}), flush=True)
+    r = gather({"ms_per_step": round(dt / steps * 1e3, 3), "obs_per_s": round(n * steps / dt)})
+    if rank == 0:
+        worst = max(x["ms_per_step"] for x in r)
+        print(json.dumps({"n_gpus": world, "workload": wname, "shards": shards, "ms_per_step_max": worst,
+                          "obs_per_s_total": round(n * world / worst * 1e3), "h2d_mb_per_gpu": h2d / 1e6, "d2h_mb_per_gpu": d2h / 1e6,
+                          "per_rank_ms": [x["ms_per_step"] for x in r]}), flush=True)
+if dist is not None:
+    dist.barrier()
+    dist.destroy_process_group()
