@@ -87,6 +87,34 @@ class _VecBase(Env):
             source.set_used_rows(self.path.used_rows)   # only the sampled raw rows cross PCIe, as one block per shard
         self.observation_space = Box(low=-1., high=1., shape=(self.frame_stack,) + self.obs_size, dtype=np.float32)
         self._pending = None
+        # args.async_sim: step_async hands the simulator stepping (host CPU) + the enqueueing of copies and kernels to a
+        # worker thread and returns at once; step_wait joins it.  The caller's thread is free while the simulators run
+        # (sim step t+1 overlaps whatever the caller does with the result of step t).
+        self.async_sim = bool(getattr(args, "async_sim", False))
+        self._future = None
+        self._pool = None
+        if self.async_sim:
+            from concurrent.futures import ThreadPoolExecutor
+            self._pool = ThreadPoolExecutor(max_workers=1, thread_name_prefix="agym-step")
+
+    def _submit(self, job):
+        """Runs `job` (simulators + enqueue) now, or on the step thread when async_sim is set."""
+        if self._pool is None:
+            self._pending = job()
+            return
+
+        def run():
+            if self.device.type == "cuda":
+                with torch.cuda.device(self.device):   # the current device is per thread
+                    return job()
+            return job()
+        self._future = self._pool.submit(run)
+
+    def _collect(self):
+        if self._future is not None:
+            self._pending, self._future = self._future.result(), None
+        r, self._pending = self._pending, None
+        return r
 
     def _frames_enqueued(self):
         """Tells the source that the copies reading its current staging set are in the streams."""
@@ -98,6 +126,11 @@ class _VecBase(Env):
         return self.step_wait(return_state=return_state)
 
     def close(self):
+        if self._future is not None:
+            self._future.result()
+        if self._pool is not None:
+            self._pool.shutdown(wait=True)
+            self._pool = None
         if hasattr(self.source, "close"):
             self.source.close()
 
@@ -136,16 +169,20 @@ class AtariVecEnv(_VecBase):
         state = self.path.stack() if return_state else None
         return state, self._info(np.zeros(self.num_envs))
 
-    def step_async(self, action):
-        """atari_env.py:119-133: steps the simulators (host) and enqueues copy + ingest; returns at once."""
-        fa, fb, flags, reward, done = self.source.step(action)
-        self._ingest(fa, fb, flags)
-        self._pending = (reward, done)
+    def step_async(self, action, after_ingest=None):
+        """atari_env.py:119-133: steps the simulators (host) and enqueues copy + ingest, then `after_ingest()` (the
+        wrapper's observe launch: it must follow the ingest in stream order)."""
+        def job():
+            fa, fb, flags, reward, done = self.source.step(action)
+            self._ingest(fa, fb, flags)
+            if after_ingest is not None:
+                after_ingest()
+            return reward, done
+        self._submit(job)
 
     def step_wait(self, return_state=True):
         """atari_env.py:134-148."""
-        reward, done = self._pending
-        self._pending = None
+        reward, done = self._collect()
         state = self.path.stack() if return_state else None
         return_reward = np.sign(reward) if self.clip_reward else reward
         truncated = np.zeros(self.num_envs, bool)

@@ -72,19 +72,23 @@ class DMCVecEnv(_VecBase):
         state = self.path.stack() if return_state else None
         return state, self._info(np.zeros(self.num_envs))
 
-    def step_async(self, action):
-        """dmc_env.py:211-226: steps the simulators (host) and enqueues copy + ingest; returns at once."""
+    def step_async(self, action, after_ingest=None):
+        """dmc_env.py:211-226: steps the simulators (host) and enqueues copy + ingest, then `after_ingest()`."""
         action = np.asarray(action, np.float32).reshape(self.num_envs, -1)
         assert (action >= -1.0).all() and (action <= 1.0).all()  # dmc_env.py:212
-        frames, flags, reward, done = self.source.step(action)
-        self.path.ingest_dmc(frames, flags)
-        self._frames_enqueued()
-        self._pending = (reward, done)
+
+        def job():
+            frames, flags, reward, done = self.source.step(action)
+            self.path.ingest_dmc(frames, flags)
+            self._frames_enqueued()
+            if after_ingest is not None:
+                after_ingest()
+            return reward, done
+        self._submit(job)
 
     def step_wait(self, return_state=True):
         """dmc_env.py:227-234."""
-        reward, done = self._pending
-        self._pending = None
+        reward, done = self._collect()
         state = self.path.stack() if return_state else None
         return_reward = np.sign(reward) if self.clip_reward else reward
         return state, return_reward, done, np.zeros(self.num_envs, bool), self._info(reward)

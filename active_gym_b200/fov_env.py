@@ -85,8 +85,8 @@ class RecordWrapper(Wrapper):
             info = self._add_info(info)
         return state, info
 
-    def step_async(self, action):
-        self.env.step_async(action)
+    def step_async(self, action, after_ingest=None):
+        self.env.step_async(action, after_ingest=after_ingest)
         self._action = action
 
     def step_wait(self, return_state=True, defer_record=False, full_action=None):
@@ -261,9 +261,9 @@ class FixedFovealEnv(Wrapper):
 
     def step_async(self, action):
         """Steps the simulators, then enqueues copy + ingest + fovea update + observation; returns at once."""
-        self.env.step_async(action["motor_action"])
         self._action = action
-        self._run_observe(action["sensory_action"], None, action.get("sensory_action_type"))
+        self.env.step_async(action["motor_action"],
+                            after_ingest=lambda: self._run_observe(action["sensory_action"], None, action.get("sensory_action_type")))
 
     def step_wait(self):
         """fov_env.py:209-221: collects (obs, reward, done, truncated, info) of the step submitted last."""

@@ -112,3 +112,38 @@ def test_env_returns_normalised_observations_when_obs_dtype_is_set(backend, monk
         assert obs.dtype == torch.float16 and obs.shape == env.last_obs_u8.shape
         want = (env.last_obs_u8.to(torch.float32) / 255.0).to(torch.float16)
         assert torch.equal(obs.cpu(), want.cpu())
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_async_sim_thread_gives_the_same_steps(backend, monkeypatch):
+    """args.async_sim: step_async returns before the simulators have stepped (they run, with the enqueueing of copies and
+    kernels, on the env's step thread); step_wait joins.  Same observations, counters and fovea as the synchronous env."""
+    import time
+    import active_gym_b200 as ag
+    from active_gym_b200.sources import PinnedFrameSource
+    _backend(monkeypatch, backend)
+    n = 7
+
+    class SlowSource(PinnedFrameSource):
+        def step(self, a):
+            time.sleep(0.05)
+            return super().step(a)
+
+    envs = [ag.AtariFixedFovealPeripheralEnv(_args(async_sim=flag, shards=2), num_envs=n, source=SlowSource(n, pool=3, done_every=4))
+            for flag in (False, True)]
+    for e in envs:
+        e.reset()
+    rng = np.random.default_rng(5)
+    for step in range(5):
+        act = {"motor_action": np.zeros(n, np.int64), "sensory_action": rng.integers(-10, 11, (n, 2)).astype(np.float64)}
+        t0 = time.perf_counter()
+        envs[1].step_async(act)
+        assert time.perf_counter() - t0 < 0.04, "step_async must not wait for the simulators"
+        want = envs[0].step(act)
+        got = envs[1].step_wait()
+        assert torch.equal(torch.as_tensor(got[0]).cpu(), torch.as_tensor(want[0]).cpu()), step
+        assert np.array_equal(got[1], want[1]) and np.array_equal(got[2], want[2])
+        for k in ("fov_loc", "ep_len", "reward"):
+            assert torch.equal(torch.as_tensor(got[4][k]).cpu(), torch.as_tensor(want[4][k]).cpu()), (step, k)
+    for e in envs:
+        e.close()
