@@ -59,15 +59,19 @@ def main():
         for rec in out_rows:
             w.writerow(rec)
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    sys.path.insert(0, ROOT)
+    from bench import sources_hash  # the same hash bench.py compares against: traffic is only reported for matching sources
+    sha = sources_hash()
     try:
         tj = json.load(open(tpath))
     except Exception:
         tj = {}
-    tj.setdefault(workload, {})
+    if tj.get("sources_sha16") != sha:  # captured on other kernel sources: start over
+        tj = {"sources_sha16": sha, "workloads": {}, "source": {}}
+    tj["workloads"].setdefault(workload, {})
     for kind, v in traffic.items():
-        tj[workload][kind] = sum(v) / len(v)
-    tj["_source"] = tj.get("_source", {})
-    tj["_source"][workload] = f"ncu --set full, {os.path.basename(rep)} ({tag}); dram__bytes_read.sum + dram__bytes_write.sum per launch"
+        tj["workloads"][workload][kind] = sum(v) / len(v)
+    tj["source"][workload] = f"ncu --set full, {os.path.basename(rep)} ({tag}); dram__bytes_read.sum + dram__bytes_write.sum per launch"
     json.dump(tj, open(tpath, "w"), indent=1, sort_keys=True)
     print(path, tpath, {k: sum(v) / len(v) for k, v in traffic.items()})
 
