@@ -169,14 +169,17 @@ class AtariVecEnv(_VecBase):
         state = self.path.stack() if return_state else None
         return state, self._info(np.zeros(self.num_envs))
 
-    def step_async(self, action, after_ingest=None):
-        """atari_env.py:119-133: steps the simulators (host) and enqueues copy + ingest, then `after_ingest()` (the
-        wrapper's observe launch: it must follow the ingest in stream order)."""
+    def step_async(self, action, after_ingest=None, before_ingest=None):
+        """atari_env.py:119-133: steps the simulators (host), calls `before_ingest(reward, done)` (the wrappers upload
+        their small host arrays ahead of the frames), enqueues copy + ingest, then `after_ingest(reward, done)` (the
+        wrappers' observe / record launches: they must follow the ingest in stream order)."""
         def job():
             fa, fb, flags, reward, done = self.source.step(action)
+            if before_ingest is not None:
+                before_ingest(reward, done)
             self._ingest(fa, fb, flags)
             if after_ingest is not None:
-                after_ingest()
+                after_ingest(reward, done)
             return reward, done
         self._submit(job)
 

@@ -281,6 +281,9 @@ __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;"
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src));
 }
+__device__ __forceinline__ void cp_async16_s(uint32_t smem_addr, const void *gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gmem_src));
+}
 __device__ __forceinline__ void cp_async4(void *smem_dst, const void *gmem_src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src));
 }
@@ -389,6 +392,8 @@ const bool g_disable_tma = getenv("AGYM_NO_TMA") != nullptr;
 const bool g_flex_old = getenv("AGYM_FLEX_OLD") != nullptr;
 // AGYM_CROP_OLD=1 forces the byte-gather crop kernel (A/B comparisons)
 const bool g_crop_old = getenv("AGYM_CROP_OLD") != nullptr;
+// AGYM_STD_NOFS=1: the standard-geometry peripheral kernel stages the fovea with per-thread 4-byte copies (A/B comparisons)
+const bool g_std_nofs = getenv("AGYM_STD_NOFS") != nullptr;
 // AGYM_INGEST_UNITS=n: units (shared-memory stages) per env of the TMA ingest kernel (tuning)
 const int g_units = getenv("AGYM_INGEST_UNITS") ? atoi(getenv("AGYM_INGEST_UNITS")) : 0;
 

@@ -513,7 +513,13 @@ __device__ __forceinline__ void prefetch_rows_imm(uint32_t rows, uint32_t dst, c
     }
 }
 
-template <int K, int NW>  // NW: words per staged fovea row, (f_w + 3) / 4 + 1, when baked in; 0 = from the plan
+// FS ("full-row staging"): the sharp fovea bytes are staged as 16-byte chunks at the positions they have in the ring
+// (the staging buffer of a frame mirrors the ring words [lr * 21 & ~3, ...) of its slot, so a chunk copy is aligned on
+// both sides and the paste reads word (row r, quad q) at an immediate offset).  Only the chunks that meet the fovea
+// columns are copied: K * f_h * 3 copies of 16 bytes per env, about one per thread and a dozen instructions each,
+// instead of up to 21 predicated 4-byte copies per thread (a quarter of the kernel's instructions).  Costs 2.5 KB of
+// shared memory per frame and buffer; used when two CTAs still fit an SM (the standard 30x30 fovea does).
+template <int K, int NW, bool FS>  // NW: words per staged fovea row, (f_w + 3) / 4 + 1, when baked in; 0 = from the plan
 __global__ void __launch_bounds__(((StdGeom::Q * StdGeom::SEG * K + 31) / 32) * 32, 2)
     k_observe_peripheral_std(const __grid_constant__ DevPlan p, const __grid_constant__ ExpandStd ew,
                              const uint8_t *__restrict__ ring, const int32_t *__restrict__ head,
@@ -530,8 +536,9 @@ __global__ void __launch_bounds__(((StdGeom::Q * StdGeom::SEG * K + 31) / 32) * 
     const int tid = threadIdx.x;
     const int N = p.N, f_h = p.f_h, f_w = p.f_w, G = gridDim.x;
     const int nw_max = NW ? NW : (f_w + 3) / 4 + 1;
-    const int buf_words = K * PP + ((K * f_h * nw_max + 3) & ~3);
-    float *bufs = reinterpret_cast<float *>(smem);  // [NBUF]{ sq [K slots][P][P] | fov [K][f_h][nw_max] }
+    const int rowbuf = (f_h * Q + 9) & ~3;          // FS: staged words of one frame (alignment slack on both sides)
+    const int buf_words = K * PP + (FS ? K * rowbuf : ((K * f_h * nw_max + 3) & ~3));
+    float *bufs = reinterpret_cast<float *>(smem);  // [NBUF]{ sq [K slots][P][P] | fov [K][f_h][nw_max] or [K][rowbuf] }
     uint32_t *tiles = reinterpret_cast<uint32_t *>(bufs + NBUF * buf_words);  // [2][K][S][S / 4] output words
     const uint32_t *ring_w = reinterpret_cast<const uint32_t *>(ring);
 
@@ -589,6 +596,20 @@ __global__ void __launch_bounds__(((StdGeom::Q * StdGeom::SEG * K + 31) / 32) * 
     const int so_t6 = (row_first + 6 > P - 1 ? P - 1 : row_first + 6) * P + base;  // t = 6
     const uint32_t bufs_s = smem_u32(bufs);
     const uint32_t word0 = (uint32_t)(g * R) * Q + q;  // this thread's first output word inside a plane
+    // FS: the (at most two) 16-byte chunks this thread stages for every env: chunk c of fovea row y of frame k
+    constexpr int NJ = 2;
+    int ck_row[NJ], ck_k[NJ], ck_c4[NJ];
+    if constexpr (FS) {
+        const int cpr = (f_w + 14) / 16 + 1, total = K * f_h * cpr;
+#pragma unroll
+        for (int a = 0; a < NJ; ++a) {
+            const int i = tid + a * (int)blockDim.x;
+            const int row = i / cpr, kk = row / f_h;
+            ck_k[a] = i < total ? kk : -1;
+            ck_row[a] = (row - kk * f_h) * Q;
+            ck_c4[a] = (i - row * cpr) * 4;
+        }
+    }
 
     // one bit per row r of this segment that meets the fovea at (lr, lc); 0 if the quad misses it
     auto fovea_rows = [&](int lr, int lc, uint32_t &mask) {
@@ -608,7 +629,22 @@ __global__ void __launch_bounds__(((StdGeom::Q * StdGeom::SEG * K + 31) / 32) * 
             mbar_expect_tx(&full[b], K * PP * 4);
             bulk_g2s(bufs + b * buf_words, pcache + (size_t)env * (K * PP), K * PP * 4, &full[b]);
         }
-        if (active) {
+        if constexpr (FS) {
+            const int4 lh = s_loc[j & (LOC_RING - 1)];
+            const int top = lh.x * Q, wb = top & ~3;           // ring word (inside a plane) the staging buffers start at
+            const int lw = lh.y >> 2, lastw = (lh.y + f_w - 1) >> 2;
+#pragma unroll
+            for (int a = 0; a < NJ; ++a) {
+                if (ck_k[a] < 0) continue;
+                const int rowbase = top + ck_row[a];
+                const int cw = ((rowbase + lw) & ~3) + ck_c4[a];  // an aligned chunk that starts inside the plane ends inside it
+                if (cw > rowbase + lastw) continue;
+                int slot = lh.z + 1 + ck_k[a];
+                slot -= slot >= K ? K : 0;
+                cp_async16_s(bufs_s + (uint32_t)(b * buf_words + K * PP + ck_k[a] * rowbuf + (cw - wb)) * 4u,
+                             ring_w + ((size_t)env * K + slot) * PLANE_W + cw);
+            }
+        } else if (active) {
             const int4 lh = s_loc[j & (LOC_RING - 1)];
             uint32_t mask;
             const uint32_t rows = fovea_rows(lh.x, lh.y, mask);
@@ -643,6 +679,10 @@ __global__ void __launch_bounds__(((StdGeom::Q * StdGeom::SEG * K + 31) / 32) * 
             if (e0 + j * G < N) prefetch(e0 + j * G, j);
             cp_async_commit();
         }
+        if constexpr (FS) {   // chunks are staged by other threads than the ones that paste them
+            cp_async_wait<DIST - 1>();
+            __syncthreads();
+        }
     }
     int it = 0;
     for (int e = blockIdx.x; e < N; e += G, ++it) {
@@ -650,7 +690,7 @@ __global__ void __launch_bounds__(((StdGeom::Q * StdGeom::SEG * K + 31) / 32) * 
         cp_async_commit();
         if ((it & 31) == 0 && tid < 32) loc_batch(it + 32);
         const int b = it % NBUF;
-        cp_async_wait<DIST>();                       // this thread's own fovea words of env e
+        if constexpr (!FS) cp_async_wait<DIST>();    // this thread's own fovea words of env e
         mbar_wait(&full[b], (it / NBUF) & 1);        // the env's cached squeeze (TMA)
         uint32_t *tile = tiles + (it & 1) * (K * PLANE_W);
         if (active) {
@@ -660,7 +700,9 @@ __global__ void __launch_bounds__(((StdGeom::Q * StdGeom::SEG * K + 31) / 32) * 
             int slot = lh.z + 1 + k;
             slot -= slot >= K ? K : 0;
             const float *sq = bufs + b * buf_words + slot * PP;
-            const uint32_t *sh = reinterpret_cast<const uint32_t *>(bufs + b * buf_words + K * PP) + fovea_pos(lh.x, lh.y);
+            const uint32_t *sh = reinterpret_cast<const uint32_t *>(bufs + b * buf_words + K * PP) +
+                                 (FS ? k * rowbuf + (int)word0 - ((lh.x * Q) & ~3) : fovea_pos(lh.x, lh.y));
+            constexpr int SHP = FS ? Q : 0;   // staged words between two rows (FS: the ring's own pitch)
             uint32_t *o = tile + k * PLANE_W + word0;
             uint64_t a0, a1, b0, b1, d0 = 0, d1 = 0;
             t_row(sq, so_t0, a0, a1);
@@ -683,7 +725,7 @@ __global__ void __launch_bounds__(((StdGeom::Q * StdGeom::SEG * K + 31) / 32) * 
                 unpack2(ffma2(w2, d1, b1), u2, u3);
                 uint32_t word = __byte_perm(__byte_perm(u0, u1, 0x0051), __byte_perm(u2, u3, 0x0051), 0x5410);
                 if (rows & (1u << r))  // fovea rows: paste the sharp bytes (fov_env.py:385-386)
-                    word = (word & ~fov_mask) | (sh[r * nw_max] & fov_mask);
+                    word = (word & ~fov_mask) | (sh[FS ? r * SHP : r * nw_max] & fov_mask);
                 o[r * Q] = word;
             }
         }
@@ -691,6 +733,7 @@ __global__ void __launch_bounds__(((StdGeom::Q * StdGeom::SEG * K + 31) / 32) * 
         // this iteration's tile buffer's twin before anyone writes it again (next iteration)
         fence_async_smem();
         if (tid == 0) bulk_wait_read<0>();
+        if constexpr (FS) cp_async_wait<DIST - 1>();   // this thread's chunks of the NEXT env, visible to all after the barrier
         __syncthreads();
         if (tid == 0) {
             bulk_s2g(out + (size_t)e * (K * PLANE_W * 4), tile, K * PLANE_W * 4);
@@ -760,27 +803,36 @@ cudaError_t launch_observe_peripheral(const DevPlan &p0, const ExpandStd *ew, co
         (reinterpret_cast<uintptr_t>(out) & 15) == 0 && (reinterpret_cast<uintptr_t>(pcache) & 15) == 0) {  // TMA bulk copies
         const int nw_max = (p.f_w + 3) / 4 + 1;
         const size_t fov_words = ((size_t)p.K * p.f_h * nw_max + 3) & ~size_t(3);
-        const size_t fs = 4 * (3 * ((size_t)p.K * 400 + fov_words) + 2 * (size_t)p.K * 1764);
+        size_t fs = 4 * (3 * ((size_t)p.K * 400 + fov_words) + 2 * (size_t)p.K * 1764);
+        // full-row staging (FS): 16-byte chunk copies; taken when two CTAs still fit an SM and two chunks per thread suffice
+        const size_t fs_rows = 4 * (3 * ((size_t)p.K * 400 + (size_t)p.K * ((p.f_h * 21 + 9) & ~3)) + 2 * (size_t)p.K * 1764);
+        const int std_threads = ((21 * 4 * p.K + 31) / 32) * 32;
+        const bool full_rows = !g_std_nofs && fs_rows <= 112 * 1024 && p.K * p.f_h * ((p.f_w + 14) / 16 + 1) <= 2 * std_threads;
         int dev = 0, sms = 148, occ = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-#define AGYM_LAUNCH_STD(KK, NW)                                                                                    \
+#define AGYM_LAUNCH_STD(KK, NW, FSV)                                                                               \
     {                                                                                                              \
     if (fs <= 220 * 1024) {                                                                                        \
         const int threads = ((21 * 4 * KK + 31) / 32) * 32;                                                        \
-        if ((e = set_smem(k_observe_peripheral_std<KK, NW>, fs)) != cudaSuccess) return e;                         \
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_observe_peripheral_std<KK, NW>, threads, fs);        \
+        if ((e = set_smem(k_observe_peripheral_std<KK, NW, FSV>, fs)) != cudaSuccess) return e;                    \
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_observe_peripheral_std<KK, NW, FSV>, threads, fs);   \
         if (occ >= 1) {                                                                                            \
-            k_observe_peripheral_std<KK, NW><<<std::min(p.N, sms * occ), threads, fs, st>>>(                       \
+            k_observe_peripheral_std<KK, NW, FSV><<<std::min(p.N, sms * occ), threads, fs, st>>>(                  \
                 p, *ew, ring, head, pcache, action, ctrl, loc, out);                                               \
             return cudaGetLastError();                                                                             \
         }                                                                                                          \
     }                                                                                                              \
     }
-        if (p.K == 4 && nw_max == 9) AGYM_LAUNCH_STD(4, 9)
-        else if (p.K == 4) AGYM_LAUNCH_STD(4, 0)
-        else if (nw_max == 9) AGYM_LAUNCH_STD(3, 9)
-        else AGYM_LAUNCH_STD(3, 0)
+        if (full_rows) {
+            fs = fs_rows;
+            if (p.K == 4) AGYM_LAUNCH_STD(4, 0, true)
+            else AGYM_LAUNCH_STD(3, 0, true)
+        }
+        else if (p.K == 4 && nw_max == 9) AGYM_LAUNCH_STD(4, 9, false)
+        else if (p.K == 4) AGYM_LAUNCH_STD(4, 0, false)
+        else if (nw_max == 9) AGYM_LAUNCH_STD(3, 9, false)
+        else AGYM_LAUNCH_STD(3, 0, false)
 #undef AGYM_LAUNCH_STD
     }
     if (pcache && p.fast_expand && quads <= 64 && (p.p_h * p.p_w) % 4 == 0) {

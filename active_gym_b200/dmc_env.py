@@ -72,17 +72,20 @@ class DMCVecEnv(_VecBase):
         state = self.path.stack() if return_state else None
         return state, self._info(np.zeros(self.num_envs))
 
-    def step_async(self, action, after_ingest=None):
-        """dmc_env.py:211-226: steps the simulators (host) and enqueues copy + ingest, then `after_ingest()`."""
+    def step_async(self, action, after_ingest=None, before_ingest=None):
+        """dmc_env.py:211-226: steps the simulators (host), `before_ingest(reward, done)`, enqueues copy + ingest, then
+        `after_ingest(reward, done)` (see AtariVecEnv.step_async)."""
         action = np.asarray(action, np.float32).reshape(self.num_envs, -1)
         assert (action >= -1.0).all() and (action <= 1.0).all()  # dmc_env.py:212
 
         def job():
             frames, flags, reward, done = self.source.step(action)
+            if before_ingest is not None:
+                before_ingest(reward, done)
             self.path.ingest_dmc(frames, flags)
             self._frames_enqueued()
             if after_ingest is not None:
-                after_ingest()
+                after_ingest(reward, done)
             return reward, done
         self._submit(job)
 

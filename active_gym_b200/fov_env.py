@@ -85,22 +85,35 @@ class RecordWrapper(Wrapper):
             info = self._add_info(info)
         return state, info
 
-    def step_async(self, action, after_ingest=None):
-        self.env.step_async(action, after_ingest=after_ingest)
-        self._action = action
+    def step_async(self, action, after_ingest=None, before_ingest=None, full_action=None):
+        """Everything of the step is enqueued here, in stream order: [reward / done upload] -> frames -> ingest ->
+        `after_ingest` (the wrapper above moves the fovea and observes) -> counters + trace (fov_env.py:27-46).  Nothing
+        is left for ``step_wait`` to enqueue: a second env group's frame copies queued in between would delay it."""
+        self._action = action if full_action is None else full_action
+        base = self.env.unwrapped
 
-    def step_wait(self, return_state=True, defer_record=False, full_action=None):
+        def before(reward, done):
+            self._path.prestage(raw_reward=reward, done=done)
+            if before_ingest is not None:
+                before_ingest(reward, done)
+
+        def after(reward, done):
+            if after_ingest is not None:
+                after_ingest(reward, done)
+            log = None
+            if self.record:
+                ret = np.sign(reward) if getattr(base, "clip_reward", False) else reward
+                log = dict(action=self._action, return_reward=np.array(ret), raw_reward=np.array(reward), done=np.array(done, bool))
+            self._deferred = (dict(raw_reward=reward, done=done, is_reset=False), log)
+            self._commit(with_res=self._with_res)
+
+        self.env.step_async(action, after_ingest=after, before_ingest=before)
+
+    def step_wait(self, return_state=True):
         state, return_reward, done, truncated, info = self.env.step_wait(return_state=return_state)
-        raw = info.get("raw_reward", return_reward)
-        log = None
-        if self.record:
-            log = dict(action=full_action if full_action is not None else self._action, return_reward=np.array(return_reward),
-                       raw_reward=np.array(raw), done=np.array(done, bool))
-        self._deferred = (dict(raw_reward=raw, done=done, is_reset=False), log)
-        if not defer_record:
-            self._commit()
-            info = self._add_info(info)
-        return state, return_reward, done, truncated, info
+        if self.host_obs:
+            self._path.sync()   # the pinned counters are valid once the shard streams are idle
+        return state, return_reward, done, truncated, self._add_info(info)
 
     def step(self, action, return_state=True):
         self.step_async(action)
@@ -260,22 +273,23 @@ class FixedFovealEnv(Wrapper):
         return obs, self._fov_info(info)
 
     def step_async(self, action):
-        """Steps the simulators, then enqueues copy + ingest + fovea update + observation; returns at once."""
+        """Steps the simulators, then enqueues the action upload, copy + ingest, fovea update + observation and the
+        record update; returns at once."""
         self._action = action
+        sa, sat = action["sensory_action"], action.get("sensory_action_type")
+        rec = self._rec
+        kw = {}
+        if rec is not None:
+            rec._with_res = self._with_res
+            kw["full_action"] = action
         self.env.step_async(action["motor_action"],
-                            after_ingest=lambda: self._run_observe(action["sensory_action"], None, action.get("sensory_action_type")))
+                            before_ingest=lambda reward, done: self.path.prestage(action=sa, action_type=sat),
+                            after_ingest=lambda reward, done: self._run_observe(sa, None, sat), **kw)
 
     def step_wait(self):
         """fov_env.py:209-221: collects (obs, reward, done, truncated, info) of the step submitted last."""
-        rec = self._rec
-        kw = dict(defer_record=True, full_action=self._action) if rec is not None else {}
-        _, reward, done, truncated, info = self.env.step_wait(return_state=False, **kw)
-        if rec is not None:
-            rec._with_res = self._with_res
-            rec._commit(with_res=self._with_res)
+        _, reward, done, truncated, info = self.env.step_wait(return_state=False)
         obs = self._result_obs()
-        if rec is not None:
-            info = rec._add_info(info)
         self._raise_device_errors()
         return obs, reward, done, truncated, self._fov_info(info)
 

@@ -14,6 +14,7 @@ the host until the shards are idle (needed before reading pinned outputs).
 """
 from __future__ import annotations
 
+import collections
 from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -129,13 +130,12 @@ class PipelinedPath:
         # staging, allocated on first use: device copies of host inputs, pinned copies of small host arrays
         self._d_frames = {}
         self._d_small = {}
-        self._h_small = {}
         self._h_out = {}
-        self._turn = 0
-        self._stage_evs = [None, None]
-        self._keep = [[], []]
+        self._stage = {}        # key -> [use counter, [pinned buffer A, B], [events of the copies that last read A, B]]
+        self._keep = collections.deque(maxlen=16)   # device-side conversion temporaries the shard streams may still read
         self._d_out = {}
         self._h_err, self._err_ev = None, None
+        self._pre = {}          # key -> (the caller's object, per-shard device slices): small arrays uploaded ahead of the frames
         self.h2d_bytes = 0  # bytes copied host -> device / device -> host since the last reset_counters()
         self.d2h_bytes = 0
         torch.cuda.synchronize(dev)  # the fills above ran on the current stream; shard streams start after them
@@ -201,28 +201,11 @@ class PipelinedPath:
                 with torch.cuda.stream(self.streams[i]):
                     yield i, lo, hi
 
-    def _begin_host_stage(self) -> int:
-        """Pinned staging of small host arrays is double buffered: before a set is rewritten, wait for the copies
-        that last read it (the host may run at most one call ahead of the device)."""
-        self._turn ^= 1
-        evs = self._stage_evs[self._turn]
-        if evs is not None:
-            for e in evs:
-                e.synchronize()
-        self._keep[self._turn] = []  # conversion temporaries of that call are no longer in use
-        return self._turn
-
-    def _end_host_stage(self, turn: int) -> None:
-        evs = self._stage_evs[turn]
-        if evs is None:
-            evs = self._stage_evs[turn] = [torch.cuda.Event() for _ in self.ranges]
-        cur = torch.cuda.current_stream(self.device)
-        for i, e in enumerate(evs):
-            e.record(cur if self.streams is None else self.streams[i])
-
-    def _small_to_device(self, key: str, value, dtype: torch.dtype, width: Optional[int], turn: int) -> Optional[List[torch.Tensor]]:
+    def _small_to_device(self, key: str, value, dtype: torch.dtype, width: Optional[int]) -> Optional[List[torch.Tensor]]:
         """(N,) / (N, width) per-env array -> one contiguous device slice per shard.  Device tensors are sliced in
-        place; host arrays go through double-buffered pinned staging + an async copy on the shard's stream."""
+        place; host arrays go through pinned staging + an async copy on the shard's stream.  The pinned staging of
+        every key is double buffered with its own events: a buffer is rewritten only after the copies that read it
+        two uses ago have completed — in a running pipeline they always have, so the host never blocks here."""
         if value is None:
             return None
         shape = (self.n_envs,) if width is None else (self.n_envs, width)
@@ -230,23 +213,56 @@ class PipelinedPath:
             t = value.detach().reshape(shape)
             if t.dtype != dtype or not t.is_contiguous():
                 t = t.to(dtype).contiguous()
-            self._keep[turn].append(t)  # possibly a temporary made on the caller's stream, read on the shard streams
+            self._keep.append(t)  # possibly a temporary made on the caller's stream, read on the shard streams
             return [t[lo:hi] for lo, hi in self.ranges]
-        hk = (key, turn)
-        if hk not in self._h_small:
-            self._h_small[hk] = _pin(shape, dtype)
-        if key not in self._d_small:
+        st = self._stage.get(key)
+        if st is None:
+            st = self._stage[key] = [0, [_pin(shape, dtype), _pin(shape, dtype)], [None, None]]
             self._d_small[key] = torch.empty(shape, dtype=dtype, device=self.device)
-        h = self._h_small[hk]
+        st[0] ^= 1
+        which = st[0]
+        h, evs = st[1][which], st[2][which]
+        if evs is not None:
+            for e in evs:
+                e.synchronize()
+        else:
+            evs = st[2][which] = [torch.cuda.Event() for _ in self.ranges]
         src = value.detach().cpu().numpy() if isinstance(value, torch.Tensor) else np.asarray(value)
         h.numpy()[...] = src.reshape(shape)
         d = self._d_small[key]
         out = []
         for i, lo, hi in self._shards():
             d[lo:hi].copy_(h[lo:hi], non_blocking=True)
+            evs[i].record(torch.cuda.current_stream(self.device))
             out.append(d[lo:hi])
         self.h2d_bytes += h.numel() * h.element_size()
         return out
+
+    _PRE = {"act": (torch.float64, 2), "atype": (torch.int32, None), "raw_reward": (torch.float64, None), "done": (torch.uint8, None)}
+
+    def prestage(self, action=None, action_type=None, raw_reward=None, done=None) -> None:
+        """Uploads the step's small per-env HOST arrays now — before the frames are enqueued.  Copies of one direction
+        are served in issue order, so an action array enqueued after 55 MB of frames per shard would hold back the
+        observe launch (and the copies back) of EVERY shard until the last frame byte has crossed the link.  The later
+        ``observe_*`` / ``record_step`` call finds the device copy by the identity of the object passed here."""
+        vals = {"act": action, "atype": action_type, "raw_reward": raw_reward, "done": done}
+        vals = {k: v for k, v in vals.items() if v is not None and not (isinstance(v, torch.Tensor) and v.device.type == "cuda")}
+        if not vals:
+            return
+        self._fork()
+        for k, v in vals.items():
+            dt, width = self._PRE[k]
+            src = _as_u8(v) if k == "done" else v
+            self._pre[k] = (v, self._small_to_device(k, src, dt, width))
+
+    def _small(self, key: str, value, dtype: torch.dtype, width: Optional[int]):
+        """`_small_to_device`, unless `value` is the object `prestage` already uploaded for this step."""
+        pre = self._pre.pop(key, None)
+        if pre is not None and pre[0] is value:
+            return pre[1]
+        if key == "done" and value is not None:
+            value = _as_u8(value)
+        return self._small_to_device(key, value, dtype, width)
 
     def _h2d_rows(self, dst: torch.Tensor, src: torch.Tensor, lo: int, hi: int) -> None:
         """Rows g of envs [lo, hi) of full host frames with (g % P) inside the cyclic run [o, o + L) -> dst, in row order."""
@@ -271,9 +287,10 @@ class PipelinedPath:
         if err:
             raise RuntimeError(f"packed H2D copy failed: cudaError {err}")
 
-    def _frames_to_device(self, key: str, frames, packed: bool):
-        """Raw frames -> per shard (device tensor, is_packed).  Device frames are sliced; host frames are copied into
-        a per-key staging tensor (only the sampled rows when the source already packs them or the rows are periodic)."""
+    def _frames_plan(self, key: str, frames, packed: bool):
+        """Validates raw frames and returns a per-shard copier: ``stage(i, lo, hi) -> (device tensor, is_packed)``, to be
+        called on shard i's stream.  Device frames are sliced; host frames are copied into a per-key staging tensor
+        (only the sampled rows when the source already packs them or the rows are periodic)."""
         h, w, c = self.raw_shape
         t = torch.as_tensor(frames)
         if c == 1 and t.dim() == 4 and t.shape[-1] == 1:
@@ -285,10 +302,9 @@ class PipelinedPath:
             raise ValueError(f"expected frames of shape {want}, got {tuple(t.shape)}")
         if t.dtype != torch.uint8:
             raise TypeError(f"expected uint8 frames, got {t.dtype}")
-        if t.device.type == "cuda":
-            t = t.contiguous()
-            return [(t[lo:hi], packed) for lo, hi in self.ranges]
         t = t.contiguous()
+        if t.device.type == "cuda":
+            return lambda i, lo, hi: (t[lo:hi], packed)
         strided = (not packed) and self.run is not None and t.is_pinned()
         dev_packed = packed or strided
         dshape = (self.n_envs, nu if dev_packed else h) + want[2:]
@@ -296,29 +312,30 @@ class PipelinedPath:
         if dk not in self._d_frames:
             self._d_frames[dk] = torch.empty(dshape, dtype=torch.uint8, device=self.device)
         d = self._d_frames[dk]
-        out = []
-        for i, lo, hi in self._shards():
+        self.h2d_bytes += d.numel()
+
+        def stage(i, lo, hi):
             if strided:
                 self._h2d_rows(d[lo:hi], t, lo, hi)
             else:
                 d[lo:hi].copy_(t[lo:hi], non_blocking=True)
-            out.append((d[lo:hi], dev_packed))
-        self.h2d_bytes += d.numel()
-        return out
+            return d[lo:hi], dev_packed
+        return stage
 
     # ------------------------------------------------------------------ ingest
     def ingest_atari(self, frames_a, frames_b, flags, packed: bool = False) -> None:
         """AtariEnv._get_state + frame logic of _step/_reset (atari_env.py:73-75, 121-133) on every shard.
         ``packed``: the frames hold only ``used_rows`` (N, 168, 160[, 3])."""
         self._fork()
-        turn = self._begin_host_stage()
-        fa = self._frames_to_device("fa", frames_a, packed)
-        fb = fa if frames_b is frames_a else self._frames_to_device("fb", frames_b, packed)
-        fl = self._small_to_device("flags", flags, torch.uint8, None, turn)
+        fa = self._frames_plan("fa", frames_a, packed)
+        fb = None if frames_b is frames_a else self._frames_plan("fb", frames_b, packed)
+        fl = self._small_to_device("flags", flags, torch.uint8, None)
+        # shard by shard: both frames of shard i cross the link before any byte of shard i + 1, so shard i's kernels
+        # and its copies back start while the later shards are still uploading
         for i, lo, hi in self._shards():
-            (a, pk), (b, _) = fa[i], fb[i]
+            a, pk = fa(i, lo, hi)
+            b = a if fb is None else fb(i, lo, hi)[0]
             (self.paths[i].ingest_atari_packed if pk else self.paths[i].ingest_atari)(a, b, fl[i])
-        self._end_host_stage(turn)
 
     def ingest_atari_packed(self, rows_a, rows_b, flags) -> None:
         self.ingest_atari(rows_a, rows_b, flags, packed=True)
@@ -326,12 +343,10 @@ class PipelinedPath:
     def ingest_dmc(self, frames, flags) -> None:
         """DMCEnv._get_obs (pixel, grey) + stack logic (dmc_env.py:175-183, 228-230) on every shard."""
         self._fork()
-        turn = self._begin_host_stage()
-        f = self._frames_to_device("f", frames, False)
-        fl = self._small_to_device("flags", flags, torch.uint8, None, turn)
+        f = self._frames_plan("f", frames, False)
+        fl = self._small_to_device("flags", flags, torch.uint8, None)
         for i, lo, hi in self._shards():
-            self.paths[i].ingest_dmc(f[i][0], fl[i])
-        self._end_host_stage(turn)
+            self.paths[i].ingest_dmc(f(i, lo, hi)[0], fl[i])
 
     # ------------------------------------------------------------------ outputs
     def stack(self, out: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -355,14 +370,13 @@ class PipelinedPath:
         elif out is None:
             out = torch.empty(shape, dtype=torch.uint8, device=self.device)
         self._fork()
-        turn = self._begin_host_stage()
-        act = self._small_to_device("act", action, torch.float64, 2, turn)
-        at = self._small_to_device("atype", action_type, torch.int32, None, turn)
+        act = self._small("act", action, torch.float64, 2)
+        at = self._small("atype", action_type, torch.int32, None)
         if isinstance(ctrl, str):
             assert ctrl == "reset"
             ct = ["reset"] * len(self.ranges)
         else:
-            ct = self._small_to_device("ctrl", ctrl, torch.uint8, None, turn)
+            ct = self._small_to_device("ctrl", ctrl, torch.uint8, None)
         h_obs = h_loc = None
         if host_out:
             hk = (kind, variant, tuple(shape))
@@ -384,7 +398,6 @@ class PipelinedPath:
                 h_loc[lo:hi].copy_(self.loc[lo:hi], non_blocking=True)
                 if kind == "flexible":
                     h_res[lo:hi].copy_(self.res[lo:hi], non_blocking=True)
-        self._end_host_stage(turn)
         if host_out:
             self.d2h_bytes += h_obs.numel() + h_loc.numel() * 4 * (2 if kind == "flexible" else 1)
             return out, (h_obs, h_loc, h_res if kind == "flexible" else None)
@@ -415,10 +428,9 @@ class PipelinedPath:
         the observe call that produced ``loc`` / ``res``.  ``raw_reward`` (N,) float, ``done`` / ``reset_mask`` (N,) bool,
         host or device.  ``host_out``: returns pinned (ep_len, cum_reward), valid after ``sync()``."""
         self._fork()
-        turn = self._begin_host_stage()
-        rr = self._small_to_device("raw_reward", raw_reward, torch.float64, None, turn)
-        dn = self._small_to_device("done", None if done is None else _as_u8(done), torch.uint8, None, turn)
-        rm = self._small_to_device("reset_mask", None if reset_mask is None else _as_u8(reset_mask), torch.uint8, None, turn)
+        rr = self._small("raw_reward", raw_reward, torch.float64, None)
+        dn = self._small("done", done, torch.uint8, None)
+        rm = self._small_to_device("reset_mask", None if reset_mask is None else _as_u8(reset_mask), torch.uint8, None)
         h = None
         if host_out:
             if "counters" not in self._h_out:
@@ -431,7 +443,6 @@ class PipelinedPath:
             if host_out:
                 h[0][lo:hi].copy_(self.ep_len[lo:hi], non_blocking=True)
                 h[1][lo:hi].copy_(self.cum_reward[lo:hi], non_blocking=True)
-        self._end_host_stage(turn)
         if host_out:
             self.d2h_bytes += 16 * self.n_envs
             return h

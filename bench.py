@@ -448,6 +448,38 @@ def time_steps(torch, fn, steps, warmup, dist=None):
     return e0.elapsed_time(e1) / 1e3  # seconds
 
 
+def time_steps_graph(torch, wl, steps, warmup, dist=None):
+    """The same `steps` steps captured ONCE in a CUDA graph (2 * steps kernel nodes over the rotated frame batches and
+    action sets) and replayed: what a learner loop with static buffers does, and the launch path whose timing does not
+    depend on how fast this host's Python can issue launches (the DMC / crop steps are shorter than two eager launches
+    through ctypes on a loaded host).  One replay = exactly `steps` steps; returns seconds."""
+    device = wl.device
+    side = torch.cuda.Stream(device=device)
+    side.wait_stream(torch.cuda.current_stream(device))
+    with torch.cuda.stream(side):
+        for _ in range(max(warmup, 2)):   # warm-up on the capture stream (function attributes, plan state)
+            wl.step()
+    torch.cuda.current_stream(device).wait_stream(side)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=side):
+        for _ in range(steps):
+            wl.step()
+    graph.replay()   # untimed: `steps` more warm-up steps through the graph
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    graph.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    return e0.elapsed_time(e1) / 1e3
+
+
 def time_kernel(torch, fn, reps, warmup=3):
     """Average device time of one launch, events around each launch on the launching stream."""
     for _ in range(warmup):
@@ -662,15 +694,23 @@ def strong_scaling(torch, dist, device, world, global_envs=16384, instances=8, r
             "l2": f"{ws:.0f} MB of frames / ring / output per GPU over {instances} rotated env batches vs 126 MB L2"}
 
 
-def measure_device(torch, dist, device, world, wname, n, steps, warmup, peak, peak_src, traffic_db):
+def measure_device(torch, dist, device, world, wname, n, steps, warmup, peak, peak_src, traffic_db, no_graph=False):
     """Device-timed step (inputs resident in HBM), per-kernel times and the roofline of one workload."""
     wl = Workload(wname, device, n=n)
     w = wl.w
     bytes_ = algorithmic_bytes(w)
-    dt = max_over_ranks(torch, dist, device, time_steps(torch, wl.step, steps, warmup, dist))
+    dt_eager = max_over_ranks(torch, dist, device, time_steps(torch, wl.step, steps, warmup, dist))
+    dt, launch = dt_eager, "eager: one ctypes call per kernel launch"
+    if not no_graph:
+        try:
+            dt = max_over_ranks(torch, dist, device, time_steps_graph(torch, wl, steps, warmup, dist))
+            launch = f"cuda graph: the {steps} timed steps ({steps * wl.launches_per_step} kernel nodes) captured once, one replay timed"
+        except Exception as ex:   # keep the eager number rather than lose the line
+            launch = "eager (graph capture failed: " + repr(ex)[:120] + ")"
     total_envs = wl.n * world
     out = {"config": config_for(wname, wl.n, world), "value": total_envs * steps / dt, "unit": UNIT, "steps": steps,
-           "ms_per_step": dt / steps * 1e3, "gpu_launches": steps * wl.launches_per_step}
+           "ms_per_step": dt / steps * 1e3, "ms_per_step_eager": dt_eager / steps * 1e3, "launch": launch,
+           "gpu_launches": steps * wl.launches_per_step}
     kern = {}
     reps = max(steps, 10)
     for kname, fn, nb in (("ingest", wl.ingest, bytes_["ingest"]), ("observe", wl.observe, bytes_["observe"])):
@@ -762,7 +802,7 @@ def run_b200_arm(a):
 
     clocks = ClockSampler(local)
     clocks.start()
-    main, wl = measure_device(torch, dist, device, world, a.workload, a.envs, a.steps, a.warmup, peak, peak_src, traffic_db)
+    main, wl = measure_device(torch, dist, device, world, a.workload, a.envs, a.steps, a.warmup, peak, peak_src, traffic_db, a.no_graph)
     # the timed region is only tens of milliseconds: keep the same step loop running (untimed) until the
     # sampler has had about half a second under identical load, so that the clock record means something
     t_load = time.perf_counter()
@@ -779,7 +819,7 @@ def run_b200_arm(a):
         main["e2e"] = measure_e2e_leg(torch, dist, device, world, rank, a, a.workload, a.envs, max(a.steps // 2, 3))
     extra_w = {}
     for k in others:
-        r, wl = measure_device(torch, dist, device, world, k, None, a.other_steps, 3, peak, peak_src, traffic_db)
+        r, wl = measure_device(torch, dist, device, world, k, None, a.other_steps, 3, peak, peak_src, traffic_db, a.no_graph)
         wl.free()
         if not a.no_e2e:
             r["e2e"] = measure_e2e_leg(torch, dist, device, world, rank, a, k, None, max(a.other_steps // 2, 3))
@@ -794,7 +834,8 @@ def run_b200_arm(a):
     if rank == 0:
         line = {
             "metric": METRIC, "value": main["value"], "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
-            "ms_per_step": main["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": main["ms_per_step"], "ms_per_step_eager": main["ms_per_step_eager"], "launch": main["launch"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8", "data": "synthetic", "config": main["config"],
             "clocks": clk, "e2e": main.get("e2e"), "gpu_launches": main["gpu_launches"],
             "roofline": main["roofline"], "cpu_baseline": cpu.get(a.workload),
@@ -825,6 +866,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=1.5, help="wall seconds of the bounded CPU sample (x host cores = CPU work)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="time the eager launch loop only (default: the timed steps are captured in a CUDA graph; the eager time is reported next to it)")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "b200" else a.warmup
     quiet_stdout()

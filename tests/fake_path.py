@@ -85,6 +85,9 @@ class OraclePath:
     def record_events(self):
         return []
 
+    def prestage(self, action=None, action_type=None, raw_reward=None, done=None):
+        self.calls.append(("prestage",))
+
     def read_errors(self):
         return 0
 

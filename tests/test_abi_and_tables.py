@@ -124,3 +124,4 @@ def test_standard_vertical_resize_never_samples_every_fifth_raw_row():
     used = np.union1d(s0, s1)
     assert len(used) == 168 and not np.any(used % 5 == 2)
     assert set(zip(b0[0::2], b1[0::2])) == {(512, 1536)} and set(zip(b0[1::2], b1[1::2])) == {(1536, 512)}
+
