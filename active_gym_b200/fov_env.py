@@ -9,6 +9,7 @@ these classes keep only the host-side bookkeeping of the reference.
 from __future__ import annotations
 
 from enum import IntEnum
+from typing import Optional
 
 import numpy as np
 import torch
@@ -211,6 +212,23 @@ class FixedFovealEnv(Wrapper):
         if self.obs_dtype is not None and self.host_obs:
             raise ValueError("obs_dtype (normalised device observations) and host_obs (pinned u8 host observations) exclude each other")
         self.last_obs_u8 = None
+        self._out = None          # set_output(): where the observe kernels store the u8 observations
+
+    @property
+    def obs_shape(self):
+        """Shape of the batched u8 observation tensor, (N, K, h, w)."""
+        return tuple(self.path.out_shape(self._kind, self.variant))
+
+    def set_output(self, out: Optional[torch.Tensor]) -> None:
+        """The observe kernels write the u8 observations into ``out`` (``obs_shape``, contiguous) instead of a fresh
+        tensor.  ``out`` may live on ANOTHER GPU whose memory this env's device can access as a peer (NVLink): the
+        kernels' stores then cross the link themselves, there is no gather copy (``vector.ShardedVecEnv(learner_device=)``)."""
+        if out is not None:
+            if tuple(out.shape) != self.obs_shape or out.dtype != torch.uint8 or not out.is_contiguous() or not out.is_cuda:
+                raise ValueError(f"output must be a contiguous uint8 CUDA tensor of shape {self.obs_shape}")
+            if self.host_obs:
+                raise ValueError("set_output and host_obs exclude each other")
+        self._out = out
 
     # ---- state the reference exposes as attributes
     @property
@@ -228,7 +246,7 @@ class FixedFovealEnv(Wrapper):
         return torch.empty(self.path.out_shape(kind, self.variant), dtype=self.obs_dtype, device=self.path.device)
 
     def _observe(self, action, ctrl, action_type=None, norm_out=None):
-        return self.path.observe_fixed(action, variant=self.variant, ctrl=ctrl, host_out=self.host_obs, norm_out=norm_out)
+        return self.path.observe_fixed(action, variant=self.variant, ctrl=ctrl, out=self._out, host_out=self.host_obs, norm_out=norm_out)
 
     def _run_observe(self, action, ctrl, action_type=None):
         norm = self._norm_buffer()
@@ -341,8 +359,8 @@ class FlexibleFovealEnv(FixedFovealEnv):
     def _observe(self, action, ctrl, action_type=None, norm_out=None):
         self._check_res(action, action_type)
         self._device_actions = isinstance(action, torch.Tensor) and action.device.type == "cuda"
-        return self.path.observe_flexible(action, action_type, variant=self.variant, ctrl=ctrl, host_out=self.host_obs,
-                                          norm_out=norm_out)
+        return self.path.observe_flexible(action, action_type, variant=self.variant, ctrl=ctrl, out=self._out,
+                                          host_out=self.host_obs, norm_out=norm_out)
 
     def _raise_device_errors(self):
         """FOV_RES actions given as device tensors cannot be validated before the launch; the kernels report what they
@@ -383,7 +401,7 @@ class FixedFovealPeripheralEnv(FixedFovealEnv):
             raise ValueError("the base env was built from different args (peripheral_res mismatch)")
 
     def _observe(self, action, ctrl, action_type=None, norm_out=None):
-        return self.path.observe_peripheral(action, ctrl=ctrl, host_out=self.host_obs, norm_out=norm_out)
+        return self.path.observe_peripheral(action, ctrl=ctrl, out=self._out, host_out=self.host_obs, norm_out=norm_out)
 
 
 class SingleEnvAdapter:

@@ -44,6 +44,7 @@ def _rt():
         vp, sz = C.c_void_p, C.c_size_t
         _cudart.cudaMemcpy2DAsync.argtypes = [vp, sz, vp, sz, sz, sz, C.c_int, vp]
         _cudart.cudaMemcpyAsync.argtypes = [vp, vp, sz, C.c_int, vp]
+        _cudart.cudaDeviceEnablePeerAccess.argtypes = [C.c_int, C.c_uint]
     return _cudart
 
 

@@ -177,16 +177,40 @@ class FovealVectorEnv(_VectorBase):
         return f"FovealVectorEnv({type(self.env).__name__}, num_envs={self.num_envs})"
 
 
+def enable_peer_access(src: torch.device, dst: torch.device) -> None:
+    """Kernels running on ``src`` may dereference pointers into ``dst``'s memory afterwards (``cudaDeviceEnablePeerAccess``;
+    over NVLink / NVSwitch on an HGX box).  Raises when the two GPUs cannot reach each other."""
+    if src == dst:
+        return
+    if not torch.cuda.can_device_access_peer(src.index, dst.index):
+        raise RuntimeError(f"{src} cannot access {dst} as a peer")
+    from .pipeline import _rt
+    rt = _rt()
+    with torch.cuda.device(src):
+        torch.cuda.current_stream(src).synchronize()      # make sure the context exists
+        err = rt.cudaDeviceEnablePeerAccess(int(dst.index), 0)
+        if err not in (0, 704):                           # 704 = cudaErrorPeerAccessAlreadyEnabled
+            raise RuntimeError(f"cudaDeviceEnablePeerAccess({src} -> {dst}) failed: cudaError {err}")
+        if err == 704:
+            rt.cudaGetLastError()                         # clear the sticky "already enabled"
+
+
 class ShardedVecEnv:
     """``num_envs`` environments over ``devices`` (default: every visible GPU): rank-ordered contiguous env blocks,
     one batched env per device, no collective.  ``make_env(n, device, lo, hi)`` builds the env of one block
     (e.g. ``lambda n, dev, lo, hi: AtariFixedFovealPeripheralEnv(args, num_envs=n, source=make_source(lo, hi), device=dev)``).
 
-    Observations and device-resident ``info`` entries come back as one tensor per device (``ShardedVecEnv.gather``
-    concatenates them on one device over NVLink when a learner wants them together); host arrays (reward, done)
-    are concatenated in env order."""
+    Without ``learner_device`` observations and device-resident ``info`` entries come back as one tensor per device
+    (``ShardedVecEnv.gather`` concatenates them on one device with peer copies when a learner wants them together);
+    host arrays (reward, done) are concatenated in env order.
 
-    def __init__(self, make_env: Callable, num_envs: int, devices: Optional[Sequence] = None):
+    ``learner_device``: the global observation batch ``(num_envs, K, h, w)`` lives on that GPU and EVERY device's observe
+    kernel stores its env block straight into it through peer memory — the kernels' own stores (TMA bulk stores for
+    the peripheral and flexible kernels) travel over NVLink / NVSwitch while the kernel is still computing the next
+    envs, so there is no gather pass and no second copy of the observations.  ``step`` / ``reset`` then return that one
+    tensor; the learner's current stream waits (device side) for every device's step."""
+
+    def __init__(self, make_env: Callable, num_envs: int, devices: Optional[Sequence] = None, learner_device=None):
         if devices is None:
             devices = [f"cuda:{i}" for i in range(torch.cuda.device_count())]
         if not devices:
@@ -197,6 +221,31 @@ class ShardedVecEnv:
         self.envs = [make_env(hi - lo, self.devices[i], lo, hi) for i, (lo, hi) in enumerate(self.ranges)]
         self.action_space = self.envs[0].action_space
         self.observation_space = self.envs[0].observation_space
+        self.learner = None if learner_device is None else torch.device(learner_device)
+        self.obs = None
+        if self.learner is not None:
+            if self.learner.type != "cuda":
+                raise RuntimeError("learner_device must be a CUDA device")
+            if self.learner.index is None:
+                self.learner = torch.device("cuda", torch.cuda.current_device())
+            if not all(hasattr(e, "set_output") for e in self.envs):
+                raise TypeError("learner_device needs foveal envs (FixedFovealEnv and subclasses): they own the observation tensor")
+            shape = (self.num_envs,) + tuple(self.envs[0].obs_shape[1:])
+            self.obs = torch.zeros(shape, dtype=torch.uint8, device=self.learner)
+            torch.cuda.current_stream(self.learner).synchronize()   # the fill is done before any peer writes into it
+            for e, (lo, hi), d in zip(self.envs, self.ranges, self.devices):
+                d = d if d.index is not None else torch.device("cuda", torch.cuda.current_device())
+                enable_peer_access(d, self.learner)
+                e.set_output(self.obs[lo:hi])
+            self._evs = [torch.cuda.Event() for _ in self.envs]
+
+    def _learner_waits(self):
+        """The learner's current stream waits for what every device has enqueued so far (cross-device event waits)."""
+        cur = torch.cuda.current_stream(self.learner)
+        for e, ev in zip(self.envs, self._evs):
+            dev = e.path.device
+            ev.record(torch.cuda.current_stream(dev))
+            cur.wait_event(ev)
 
     def _split(self, actions, i):
         lo, hi = self.ranges[i]
@@ -214,6 +263,9 @@ class ShardedVecEnv:
 
     def reset(self, mask=None):
         res = [e.reset(mask=None if mask is None else np.asarray(mask)[lo:hi]) for e, (lo, hi) in zip(self.envs, self.ranges)]
+        if self.learner is not None:
+            self._learner_waits()
+            return self.obs, self._merge_info([r[1] for r in res])
         return [r[0] for r in res], self._merge_info([r[1] for r in res])
 
     def step_async(self, actions):
@@ -223,6 +275,9 @@ class ShardedVecEnv:
     def step_wait(self):
         res = [e.step_wait() for e in self.envs]
         obs = [r[0] for r in res]
+        if self.learner is not None:
+            self._learner_waits()
+            obs = self.obs
         reward = np.concatenate([np.asarray(r[1]) for r in res])
         done = np.concatenate([np.asarray(r[2]) for r in res])
         trunc = np.concatenate([np.asarray(r[3]) for r in res])

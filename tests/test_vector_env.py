@@ -147,3 +147,66 @@ def test_async_sim_thread_gives_the_same_steps(backend, monkeypatch):
             assert torch.equal(torch.as_tensor(got[4][k]).cpu(), torch.as_tensor(want[4][k]).cpu()), (step, k)
     for e in envs:
         e.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["peripheral", "fixed", "flexible"])
+def test_sharded_vec_env_learner_device_output_is_written_by_the_kernels(kind):
+    """ShardedVecEnv(learner_device=): every device's observe kernel stores its env block straight into ONE tensor on
+    the learner's GPU (peer memory when the devices differ; all visible GPUs are used, the same GPU three times on a
+    1-GPU box) — equal to the oracle's observation of every env, no gather copy."""
+    import active_gym_b200 as ag
+    from active_gym_b200.sources import PinnedFrameSource
+    from oracle import agym_oracle as orc
+    n, K, S, fov = 301, 4, (84, 84), (30, 30)
+    ndev = torch.cuda.device_count()
+    devices = [f"cuda:{i}" for i in range(ndev)] if ndev > 1 else ["cuda:0"] * 3
+    full = PinnedFrameSource(n, pool=3, seed=33)
+
+    class Block:   # rows [lo, hi) of the full source's batches
+        def __init__(s, lo, hi):
+            s.lo, s.hi, s.t, s.raw_shape, s.n_actions = lo, hi, 0, full.raw_shape, full.n_actions
+        def _next(s):
+            b = full.batches[s.t % len(full.batches)][s.lo:s.hi]; s.t += 1; return b
+        def reset(s, mask=None):
+            f = s._next(); return f, f, np.full(s.hi - s.lo, 5, np.uint8)
+        def step(s, a):
+            return s._next(), s._next(), np.full(s.hi - s.lo, 3, np.uint8), np.zeros(s.hi - s.lo), np.zeros(s.hi - s.lo, bool)
+
+    make = {"peripheral": ag.AtariFixedFovealPeripheralEnv, "fixed": ag.AtariFixedFovealEnv, "flexible": ag.AtariFlexibleFovealEnv}[kind]
+    args = _args(shards=2, mask_out=(kind == "flexible"))
+    sh = ag.ShardedVecEnv(lambda m, d, lo, hi: make(args, num_envs=m, source=Block(lo, hi), device=d), n, devices=devices,
+                          learner_device="cuda:0")
+    ring, head = orc.new_state(n, K, S)
+    loc = np.tile(np.array([4, 6], np.int32), (n, 1))
+    res = np.tile(np.array(fov, np.int32), (n, 1))
+
+    def want():
+        if kind == "peripheral":
+            return orc.observe_peripheral(ring, head, loc, fov, (20, 20))
+        if kind == "flexible":
+            return orc.observe_flexible(ring, head, loc, res, fov, variant="mask")
+        return orc.observe_fixed(ring, head, loc, fov, variant="crop").astype(np.float64)
+
+    tol = 0.0 if kind == "fixed" else 0.5 + 1e-2
+    obs, info = sh.reset()
+    assert obs is sh.obs and obs.device == torch.device("cuda:0") and tuple(obs.shape)[0] == n
+    b = full.batches[0].numpy()
+    orc.ingest_atari(b, b, np.full(n, 5, np.uint8), ring, head, orc.LUMA_RGB)
+    torch.cuda.current_stream(obs.device).synchronize()
+    assert np.abs(obs.cpu().numpy().astype(np.float64) - want()).max() <= tol
+    rng = np.random.default_rng(5)
+    t = 1
+    for step in range(3):
+        sa = rng.integers(-10, 11, (n, 2)).astype(np.float64)
+        act = {"motor_action": np.zeros(n, np.int64), "sensory_action": sa, "sensory_action_type": np.zeros(n, np.int64)}
+        obs, r, d, tr, info = sh.step(act)
+        nb = len(full.batches)
+        fa, fb = full.batches[t % nb].numpy(), full.batches[(t + 1) % nb].numpy()
+        t += 2
+        orc.ingest_atari(fa, fb, np.full(n, 3, np.uint8), ring, head, orc.LUMA_RGB)
+        orc.update_loc(sa, loc, obs_size=S, fov_size=fov, relative=True, lo=-10.0, hi=10.0,
+                       **(dict(atype=np.zeros(n, np.int32), res=res) if kind == "flexible" else {}))
+        torch.cuda.current_stream(obs.device).synchronize()   # the learner's stream already waits for every device
+        assert np.abs(obs.cpu().numpy().astype(np.float64) - want()).max() <= tol, (kind, step)
+    sh.close()
