@@ -21,6 +21,7 @@
 #include <cuda_fp16.h>
 
 #include <algorithm>
+#include <utility>
 #include <cstdlib>
 #include <cstring>
 
@@ -277,6 +278,15 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
 // barrier among the consumer warps only (the producer warp never joins it)
 __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kThreads) : "memory"); }
 
+// ---- programmatic dependent launch (PDL).  A kernel launched through launch_pdl() may start while the kernel before
+// it in the stream is still draining: pdl_launch_dependents() (first statement of every such kernel) lets the NEXT
+// kernel's CTAs be scheduled as soon as SM resources free up, and pdl_wait() — executed by every thread after the
+// prologue that touches only the plan's constant tables and shared memory, and before the first access to any buffer a
+// previous kernel may have written or may still read — blocks until the previous kernel has completed and flushed.
+// What overlaps is launch latency, CTA ramp-up and the prologue; the data dependencies are unchanged.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---- cp.async (LDGSTS) helpers
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src));
@@ -383,6 +393,22 @@ cudaError_t set_smem(F func, size_t bytes) {
 }
 
 size_t a16(size_t v) { return (v + 15) & ~size_t(15); }
+
+// AGYM_NO_PDL=1: plain stream-ordered launches (A/B comparisons)
+const bool g_no_pdl = getenv("AGYM_NO_PDL") != nullptr;
+
+// <<<grid, block, smem, st>>> with the programmatic-stream-serialization attribute (see pdl_wait above).  Only for
+// kernels that execute pdl_wait() before their first dependent memory access.
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args &&...args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = g_no_pdl ? 0 : 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, KArgs(std::forward<Args>(args))...);
+}
 
 // AGYM_NO_STD=1 forces the table-driven peripheral kernel even for the standard geometry
 const bool g_disable_std = getenv("AGYM_NO_STD") != nullptr;

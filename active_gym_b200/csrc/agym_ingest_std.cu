@@ -65,6 +65,7 @@ __global__ void __launch_bounds__(kStdThreads, 3) k_ingest_gray_std(const __grid
     float *s_sqh = reinterpret_cast<float *>(s_sqq + (PC ? kPW * 8 : 0));       // [20][taps] H-pass weights
     int32_t *s_sqx = reinterpret_cast<int32_t *>(s_sqh + (PC ? kPW * p.sq_h.taps : 0));  // [20] first source row
 
+    pdl_launch_dependents();
     if (tid == 0) {
         for (int i = 0; i < NS; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], kThreads / 32); }
         mbar_fence_init();
@@ -75,6 +76,7 @@ __global__ void __launch_bounds__(kStdThreads, 3) k_ingest_gray_std(const __grid
         for (int i = tid; i < kPW; i += kStdThreads) s_sqx[i] = __ldg(p.sq_h.xmin + i);
     }
     __syncthreads();
+    pdl_wait();   // frames, flags, ring, head, pcache: not before the previous kernel in the stream has finished
 
     // unit `it` of this CTA: env = blockIdx.x + (it / 2) * gridDim.x, part = it & 1 (output rows 42 part .. 42 part + 41)
     const int my_envs = (N - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
@@ -326,8 +328,7 @@ cudaError_t launch_std(const DevPlan &p, const uint8_t *flags, uint8_t *ring, in
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kStdThreads, fs);
-    kern<<<std::min(p.N, sms * std::max(occ, 1)), kStdThreads, fs, st>>>(p, flags, ring, head, pcache, tma, tmb);
-    return cudaGetLastError();
+    return launch_pdl(kern, dim3(std::min(p.N, sms * std::max(occ, 1))), dim3(kStdThreads), fs, st, p, flags, ring, head, pcache, tma, tmb);
 }
 
 }  // namespace

@@ -554,11 +554,11 @@ __global__ void __launch_bounds__(((StdGeom::Q * StdGeom::SEG * K + 31) / 32) * 
         }
         s_loc[j & (LOC_RING - 1)] = make_int4(r, c, hh, 0);
     };
+    pdl_launch_dependents();
     if (tid == 0) {
         for (int i = 0; i < NBUF; ++i) mbar_init(&full[i], 1);
         mbar_fence_init();
     }
-    if (tid < 32) loc_batch(0);
 
     const bool active = tid < NB;
     const int q = tid % Q, t2 = tid / Q;
@@ -671,6 +671,8 @@ __global__ void __launch_bounds__(((StdGeom::Q * StdGeom::SEG * K + 31) / 32) * 
         t23 = ffma2(p2, wc23, ffma2(p1, wb23, ffma2(p0, wa23, bias2)));
     };
 
+    pdl_wait();       // ring, head, pcache, action, loc, out: not before the previous kernel in the stream has finished
+    if (tid < 32) loc_batch(0);
     __syncthreads();  // s_loc of the first 32 iterations, mbarriers initialised
     {
         const int e0 = blockIdx.x;
@@ -774,6 +776,7 @@ cudaError_t launch_observe_fixed(const DevPlan &p0, const uint8_t *ring, const i
     if (variant == AGYM_OUT_CROP && (p.K * p.f_h * p.f_w) % 4 == 0 && !g_disable_std && !g_crop_old &&
         crop_smem <= 64 * 1024 && p.K * p.f_h * crop_nwx * 4 + 4 < 65536) {
         if ((e = set_smem(k_observe_fixed_crop_v2, crop_smem)) != cudaSuccess) return e;
+        // (plain launch: see launch_ingest_dmc about programmatic dependent launch and multi-wave grids)
         k_observe_fixed_crop_v2<<<(p.N + kCropWarps - 1) / kCropWarps, kCropWarps * 32, crop_smem, st>>>(p, ring, head, action, ctrl, loc, out, crop_nwx);
         return cudaGetLastError();   // the normalised output, if any, was written by the kernel
     } else if (variant == AGYM_OUT_CROP && (p.K * p.f_h * p.f_w) % 4 == 0 && !g_disable_std) {
@@ -818,9 +821,8 @@ cudaError_t launch_observe_peripheral(const DevPlan &p0, const ExpandStd *ew, co
         if ((e = set_smem(k_observe_peripheral_std<KK, NW, FSV>, fs)) != cudaSuccess) return e;                    \
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_observe_peripheral_std<KK, NW, FSV>, threads, fs);   \
         if (occ >= 1) {                                                                                            \
-            k_observe_peripheral_std<KK, NW, FSV><<<std::min(p.N, sms * occ), threads, fs, st>>>(                  \
-                p, *ew, ring, head, pcache, action, ctrl, loc, out);                                               \
-            return cudaGetLastError();                                                                             \
+            return launch_pdl(k_observe_peripheral_std<KK, NW, FSV>, dim3(std::min(p.N, sms * occ)), dim3(threads), fs, st, \
+                              p, *ew, ring, head, pcache, action, ctrl, loc, out);                                 \
         }                                                                                                          \
     }                                                                                                              \
     }
