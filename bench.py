@@ -76,7 +76,7 @@ WORKLOADS = {
 }
 S = (84, 84)
 KERNEL_NAMES = {  # the kernels the two legs of a step launch for the benchmark geometries (GPUTEST / ncu launch lists)
-    ("atari_peripheral", "ingest"): "k_ingest_gray_std<160,true,2>", ("atari_peripheral", "observe"): "k_observe_peripheral_std<4,9>",
+    ("atari_peripheral", "ingest"): "k_ingest_gray_std<160,true,2>", ("atari_peripheral", "observe"): "k_observe_peripheral_std<4,0,true>",
     ("atari_fixed", "ingest"): "k_ingest_atari_tma<480,84,3,true,2>", ("atari_fixed", "observe"): "k_observe_fixed_crop_v2",
     ("atari_flexible", "ingest"): "k_ingest_gray_std<160,false,2>", ("atari_flexible", "observe"): "k_observe_flexible_v3<MASK>",
     ("dmc_fixed", "ingest"): "k_ingest_dmc", ("dmc_fixed", "observe"): "k_observe_fixed_crop_v2",

@@ -17,7 +17,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "active_gym_b200", "lib", "libagym_b200.so")
 HOT = {
     "k_ingest_gray_std_160_pc": r"k_ingest_gray_stdILi160ELb1ELi2E",
-    "k_observe_peripheral_std_4_9": r"k_observe_peripheral_stdILi4ELi9E",
+    "k_observe_peripheral_std_4_fs": r"k_observe_peripheral_stdILi4ELi0ELb1E",
     "k_ingest_atari_tma_rgb": r"k_ingest_atari_tmaILi480ELi84ELi3ELb1ELi2E",
     "k_observe_flexible_v3_mask": r"k_observe_flexible_v3ILi1E",
     "k_observe_fixed_crop": r"k_observe_fixed_crop_v\d",
