@@ -12,7 +12,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("AGYM_LIB") or os.path.join(_HERE, "lib", "libagym_b200.so")  # AGYM_LIB: timing experiments only
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 # status codes / flags (mirrors of the header's macros)
 OK = 0
@@ -39,6 +39,7 @@ class Config(C.Structure):
         ("raw_h", C.c_int32), ("raw_w", C.c_int32), ("raw_c", C.c_int32), ("luma_w", C.c_int32 * 3),
         ("fov_h", C.c_int32), ("fov_w", C.c_int32), ("periph_h", C.c_int32), ("periph_w", C.c_int32),
         ("relative", C.c_int32), ("act_lo", C.c_double), ("act_hi", C.c_double), ("fov_init_loc", C.c_double * 2),
+        ("no_antialias", C.c_int32),
     ]
 
 
@@ -76,8 +77,8 @@ def lib() -> C.CDLL:
     L.agym_synth_frames.argtypes = [vp, sz, u64, vp]
     L.agym_normalize.argtypes = [vp, sz, i32, vp, vp]
     L.agym_table_cv2.argtypes = [i32, i32, i32, vp, vp, vp]
-    L.agym_table_aa.argtypes = [i32, i32, vp, vp, sz, vp]
-    L.agym_table_blur.argtypes = [i32, i32, vp, vp, vp, sz, vp, vp]
+    L.agym_table_aa.argtypes = [i32, i32, i32, vp, vp, sz, vp]
+    L.agym_table_blur.argtypes = [i32, i32, i32, vp, vp, vp, sz, vp, vp]
     if L.agym_abi_version() != ABI_VERSION:
         raise RuntimeError(f"libagym_b200 ABI {L.agym_abi_version()} != expected {ABI_VERSION}; rebuild")
     _lib = L

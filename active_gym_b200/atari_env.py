@@ -57,7 +57,8 @@ def _path_from_args(args, num_envs, obs_size, raw_shape, luma, device, host_sour
         sensory_action_mode=getattr(args, "sensory_action_mode", "absolute"),
         sensory_action_space=getattr(args, "sensory_action_space", (0.0, 0.0)),
         peripheral_res=getattr(args, "peripheral_res", None), device=device,
-        cache_peripheral=getattr(args, "cache_peripheral", True), side_streams=host_source)
+        cache_peripheral=getattr(args, "cache_peripheral", True), side_streams=host_source,
+        antialias=bool(getattr(args, "antialias", True)))
 
 
 class _VecBase(Env):

@@ -51,8 +51,8 @@ struct AxisOff {
     int n_in, n_out, taps;
 };
 
-AxisOff add_axis(Pool &pool, int n_in, int n_out) {
-    const AaAxis ax = build_aa_axis(n_in, n_out);
+AxisOff add_axis(Pool &pool, int n_in, int n_out, bool aa) {
+    const AaAxis ax = build_aa_axis(n_in, n_out, aa);
     return AxisOff{pool.add_i(ax.xmin), pool.add_f(ax.w), n_in, n_out, ax.taps};
 }
 
@@ -127,6 +127,7 @@ int agym_plan_create(const agym_config *cfg, agym_plan **out_plan) {
     pl->device = dev;
     const agym_config &c = pl->cfg;
 
+    const bool aa = c.no_antialias == 0;   // torchvision Resize: antialiased (today's default) or plain bilinear
     Pool pool;
     // cv2.resize raw -> obs (atari_env.py:74).  Unused by the DMC path (raw == obs).
     const Cv2Axis cx = build_cv2_axis(c.raw_w, c.obs_w, true), cy = build_cv2_axis(c.raw_h, c.obs_h, false);
@@ -147,15 +148,15 @@ int agym_plan_create(const agym_config *cfg, agym_plan **out_plan) {
     pl->used_rows = used;
     AxisOff sq_w{}, sq_h{}, ex_w{}, ex_h{}, full_w{}, full_h{};
     if (c.periph_h > 0) {
-        sq_w = add_axis(pool, c.obs_w, c.periph_w); sq_h = add_axis(pool, c.obs_h, c.periph_h);
-        ex_w = add_axis(pool, c.periph_w, c.obs_w); ex_h = add_axis(pool, c.periph_h, c.obs_h);
+        sq_w = add_axis(pool, c.obs_w, c.periph_w, aa); sq_h = add_axis(pool, c.obs_h, c.periph_h, aa);
+        ex_w = add_axis(pool, c.periph_w, c.obs_w, aa); ex_h = add_axis(pool, c.periph_h, c.obs_h, aa);
     }
     const int s_max = c.obs_h > c.obs_w ? c.obs_h : c.obs_w;
     size_t o_flex = 0, o_flexb = 0, o_flexq = 0, o_flexh2 = 0, o_counters = 0;
     bool have_flexq = false;
     int blur_tmax = 0;
     if (c.fov_h > 0) {
-        full_w = add_axis(pool, c.fov_w, c.obs_w); full_h = add_axis(pool, c.fov_h, c.obs_h);
+        full_w = add_axis(pool, c.fov_w, c.obs_w, aa); full_h = add_axis(pool, c.fov_h, c.obs_h, aa);
         // flexible fovea: for every window size r, r->f, f->r and r->S on both axes
         std::vector<int32_t> index(static_cast<size_t>(2) * 3 * (s_max + 1) * 4, 0);
         for (int axis = 0; axis < 2; ++axis) {
@@ -163,7 +164,7 @@ int agym_plan_create(const agym_config *cfg, agym_plan **out_plan) {
             for (int fam = 0; fam < 3; ++fam)
                 for (int r = 1; r <= S; ++r) {
                     const int n_in = fam == 1 ? f : r, n_out = fam == 0 ? f : (fam == 1 ? r : S);
-                    const AxisOff a = add_axis(pool, n_in, n_out);
+                    const AxisOff a = add_axis(pool, n_in, n_out, aa);
                     int32_t *e = index.data() + (static_cast<size_t>(axis * 3 + fam) * (s_max + 1) + r) * 4;
                     e[0] = static_cast<int32_t>(a.xmin); e[1] = static_cast<int32_t>(a.w); e[2] = a.taps; e[3] = a.n_out;
                 }
@@ -174,7 +175,7 @@ int agym_plan_create(const agym_config *cfg, agym_plan **out_plan) {
         for (int axis = 0; axis < 2; ++axis) {
             const int f = axis == 0 ? c.fov_h : c.fov_w, S = axis == 0 ? c.obs_h : c.obs_w;
             for (int r = 1; r <= S; ++r) {
-                const AaAxis ax = build_blur_axis(r, f);
+                const AaAxis ax = build_blur_axis(r, f, aa);
                 int32_t *e = bindex.data() + (static_cast<size_t>(axis) * (s_max + 1) + r) * 4;
                 e[0] = static_cast<int32_t>(pool.add_i(ax.xmin)); e[1] = static_cast<int32_t>(pool.add_f(ax.w));
                 e[2] = ax.taps; e[3] = ax.n_out;
@@ -188,7 +189,7 @@ int agym_plan_create(const agym_config *cfg, agym_plan **out_plan) {
         if (blur_tmax <= 16) {
             std::vector<int32_t> qindex(static_cast<size_t>(s_max + 1) * 4, 0);
             for (int r = 1; r <= c.obs_w; ++r) {
-                const AaAxis ax = build_blur_axis(r, c.fov_w);
+                const AaAxis ax = build_blur_axis(r, c.fov_w, aa);
                 int nh = 1;
                 const std::vector<uint32_t> qu = quantize_axis_q16(ax, &nh);
                 const std::vector<int32_t> q(qu.begin(), qu.end());
@@ -200,7 +201,7 @@ int agym_plan_create(const agym_config *cfg, agym_plan **out_plan) {
             // H-axis operators with every weight stored twice ({w, w} is the FFMA2 operand), padded to 16 bytes
             std::vector<int32_t> hindex(static_cast<size_t>(s_max + 1) * 4, 0);
             for (int r = 1; r <= c.obs_h; ++r) {
-                const AaAxis ax = build_blur_axis(r, c.fov_h);
+                const AaAxis ax = build_blur_axis(r, c.fov_h, aa);
                 std::vector<float> w2;
                 for (float w : ax.w) { w2.push_back(w); w2.push_back(w); }
                 while (w2.size() % 4) w2.push_back(0.f);
@@ -243,7 +244,7 @@ int agym_plan_create(const agym_config *cfg, agym_plan **out_plan) {
     bool squeeze_q = false;
     int sq_taps4 = 0;
     if (fast_squeeze) {
-        const AaAxis ax = build_aa_axis(c.obs_w, c.periph_w);
+        const AaAxis ax = build_aa_axis(c.obs_w, c.periph_w, aa);
         sq_taps4 = (ax.taps + 3) & ~3;
         std::vector<int32_t> ofs;
         std::vector<float> wts(static_cast<size_t>(ax.n_out) * sq_taps4, 0.f);
@@ -280,7 +281,7 @@ int agym_plan_create(const agym_config *cfg, agym_plan **out_plan) {
     size_t o_ewi = 0, o_eww = 0, o_ehi = 0, o_ehw = 0, o_eww1 = 0;
     if (fast_expand) {
         auto lerp = [&](int n_in, int n_out, std::vector<int32_t> &i0, std::vector<float> &w0, std::vector<float> &w1) {
-            const AaAxis ax = build_aa_axis(n_in, n_out);
+            const AaAxis ax = build_aa_axis(n_in, n_out, aa);
             for (int i = 0; i < n_out; ++i) {
                 int first = -1, last = -1;
                 for (int j = 0; j < ax.taps; ++j)
@@ -542,9 +543,9 @@ int agym_table_cv2(int n_src, int n_dst, int zero_frac_at_border, int32_t *h_s0,
     return AGYM_OK;
 }
 
-int agym_table_aa(int n_in, int n_out, int32_t *h_xmin, float *h_w, size_t w_capacity, int32_t *taps) {
+int agym_table_aa(int n_in, int n_out, int antialias, int32_t *h_xmin, float *h_w, size_t w_capacity, int32_t *taps) {
     if (n_in <= 0 || n_out <= 0 || !h_xmin || !h_w || !taps) return AGYM_ERR_INVALID_ARG;
-    const AaAxis ax = build_aa_axis(n_in, n_out);
+    const AaAxis ax = build_aa_axis(n_in, n_out, antialias != 0);
     if (ax.w.size() > w_capacity) return AGYM_ERR_INVALID_ARG;
     std::memcpy(h_xmin, ax.xmin.data(), sizeof(int32_t) * n_out);
     std::memcpy(h_w, ax.w.data(), sizeof(float) * ax.w.size());
@@ -552,9 +553,10 @@ int agym_table_aa(int n_in, int n_out, int32_t *h_xmin, float *h_w, size_t w_cap
     return AGYM_OK;
 }
 
-int agym_table_blur(int r, int f, int32_t *h_xmin, float *h_w, uint16_t *h_q, size_t capacity, int32_t *taps, int32_t *halves) {
+int agym_table_blur(int r, int f, int antialias, int32_t *h_xmin, float *h_w, uint16_t *h_q, size_t capacity, int32_t *taps,
+                    int32_t *halves) {
     if (r <= 0 || f <= 0 || !h_xmin || !h_w || !h_q || !taps || !halves) return AGYM_ERR_INVALID_ARG;
-    const AaAxis ax = build_blur_axis(r, f);
+    const AaAxis ax = build_blur_axis(r, f, antialias != 0);
     int nh = 1;
     const std::vector<uint32_t> q = quantize_axis_q16(ax, &nh);
     if (ax.w.size() > capacity || q.size() * 2 > capacity) return AGYM_ERR_INVALID_ARG;

@@ -33,7 +33,7 @@ Cv2Axis build_cv2_axis(int n_src, int n_dst, bool zero_frac_at_border) {
 
 // ATen UpSampleKernel.cpp, _compute_indices_min_size_weights_aa with the bilinear (triangle)
 // filter, evaluated in double (the Atari reference path is float64).
-AaAxis build_aa_axis(int n_in, int n_out) {
+AaAxis build_aa_axis(int n_in, int n_out, bool antialias) {
     AaAxis ax;
     ax.n_in = n_in; ax.n_out = n_out;
     ax.xmin.resize(n_out);
@@ -44,8 +44,10 @@ AaAxis build_aa_axis(int n_in, int n_out) {
         return ax;
     }
     const double scale = static_cast<double>(n_in) / static_cast<double>(n_out);
-    const double support = scale >= 1.0 ? scale : 1.0;
-    const double inv = scale >= 1.0 ? 1.0 / scale : 1.0;
+    // without antialiasing the triangle filter keeps its unit support when downscaling: taps {floor(src), floor(src) + 1}
+    // of src = scale * (i + 0.5) - 0.5 with weights {1 - frac, frac}, i.e. ATen's upsample_bilinear2d
+    const double support = (antialias && scale >= 1.0) ? scale : 1.0;
+    const double inv = (antialias && scale >= 1.0) ? 1.0 / scale : 1.0;
     const int max_taps = static_cast<int>(std::ceil(support)) * 2 + 1;
     std::vector<int> xsize(n_out);
     std::vector<double> wd(static_cast<size_t>(n_out) * max_taps, 0.0);
@@ -86,8 +88,8 @@ AaAxis build_aa_axis(int n_in, int n_out) {
     return ax;
 }
 
-AaAxis build_blur_axis(int r, int f) {
-    const AaAxis down = build_aa_axis(r, f), up = build_aa_axis(f, r);
+AaAxis build_blur_axis(int r, int f, bool antialias) {
+    const AaAxis down = build_aa_axis(r, f, antialias), up = build_aa_axis(f, r, antialias);
     std::vector<double> dense(static_cast<size_t>(r) * r, 0.0);
     for (int y = 0; y < r; ++y)
         for (int a = 0; a < up.taps; ++a) {

@@ -29,12 +29,14 @@ struct AaAxis {
     std::vector<int32_t> xmin;     // [n_out]
     std::vector<float> w;          // [n_out][taps]
 };
-AaAxis build_aa_axis(int n_in, int n_out);
+// antialias = false: plain bilinear (ATen upsample_bilinear2d, align_corners=False) — what torchvision's Resize did on
+// tensors before antialias=True became the default; two taps per destination index.
+AaAxis build_aa_axis(int n_in, int n_out, bool antialias = true);
 
 // The flexible fovea's blur along one axis, Resize(f) followed by Resize(r) (fov_env.py:276-280), as ONE
 // banded r x r operator M = A(f -> r) * B(r -> f): the reference keeps floats between the two resamples,
 // so the composition is the same linear map (weights multiplied and summed in double).
-AaAxis build_blur_axis(int r, int f);
+AaAxis build_blur_axis(int r, int f, bool antialias = true);
 
 // The same operator in 16-bit fixed point for IDP.2A (k_observe_flexible_v3's W pass): per output index
 // `halves` groups of 8 weights (taps 0-7, 8-15, ...) starting at xmin, scaled by 2^16 and rounded by largest

@@ -39,7 +39,11 @@ class ObservationPath:
                  luma: Sequence[int] = LUMA_RGB, fov_size: Optional[Tuple[int, int]] = None,
                  fov_init_loc: Sequence[float] = (0, 0), sensory_action_mode: str = "absolute",
                  sensory_action_space: Sequence[float] = (0.0, 0.0), peripheral_res: Optional[Tuple[int, int]] = None,
-                 device: Optional[torch.device] = None, cache_peripheral: bool = True, buffers: Optional[dict] = None):
+                 device: Optional[torch.device] = None, cache_peripheral: bool = True, buffers: Optional[dict] = None,
+                 antialias: bool = True):
+        """``antialias``: how the wrappers' ``torchvision.transforms.Resize`` calls (fov_env.py:120, 248, 366-368) are
+        restated — antialiased bilinear (the installed torchvision's default, what the fixtures were recorded with) or
+        plain bilinear (the default of older torchvision releases on tensors)."""
         if not torch.cuda.is_available():
             raise RuntimeError("active_gym_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
@@ -64,6 +68,8 @@ class ObservationPath:
         lo, hi = (float(sensory_action_space[0]), float(sensory_action_space[1])) if self.relative else (0.0, 0.0)
         cfg.act_lo, cfg.act_hi = lo, hi
         cfg.fov_init_loc[:] = [float(fov_init_loc[0]), float(fov_init_loc[1])]
+        cfg.no_antialias = 0 if antialias else 1
+        self.antialias = bool(antialias)
         self._cfg = cfg
         self._L = _lib.lib()
         self._plan = C.c_void_p()

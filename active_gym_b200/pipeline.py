@@ -84,7 +84,7 @@ class PipelinedPath:
     def __init__(self, n_envs: int, frame_stack: int, obs_size, raw_shape, shards: int = 1, device=None,
                  luma: Sequence[int] = LUMA_RGB, fov_size=None, fov_init_loc=(0, 0), sensory_action_mode: str = "absolute",
                  sensory_action_space=(0.0, 0.0), peripheral_res=None, cache_peripheral: bool = True,
-                 packed_h2d: bool = True, side_streams: bool = False):
+                 packed_h2d: bool = True, side_streams: bool = False, antialias: bool = True):
         if not torch.cuda.is_available():
             raise RuntimeError("active_gym_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
@@ -115,7 +115,7 @@ class PipelinedPath:
                 ObservationPath(hi - lo, K, self.obs_size, self.raw_shape, luma=luma, fov_size=fov_size,
                                 fov_init_loc=fov_init_loc, sensory_action_mode=sensory_action_mode,
                                 sensory_action_space=sensory_action_space, peripheral_res=peripheral_res, device=dev,
-                                cache_peripheral=cache_peripheral,
+                                cache_peripheral=cache_peripheral, antialias=antialias,
                                 buffers=dict(ring=self.ring[lo:hi], head=self.head[lo:hi], loc=self.loc[lo:hi],
                                              res=self.res[lo:hi], pcache=None if self.pcache is None else self.pcache[lo:hi],
                                              err=self.err))

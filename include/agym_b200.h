@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define AGYM_ABI_VERSION 2
+#define AGYM_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define AGYM_API __attribute__((visibility("default")))
@@ -100,6 +100,8 @@ typedef struct agym_config {
     int32_t relative;            /* sensory_action_mode == "relative" (fov_env.py:114-118)     */
     double act_lo, act_hi;       /* sensory_action_space, relative mode (fov_env.py:116,170)   */
     double fov_init_loc[2];      /* fov_init_loc (fov_env.py:111,149-150)                      */
+    int32_t no_antialias;        /* 0: torchvision Resize as installed today (antialias=True, fov_env.py:120,248,366-368);
+                                    1: plain bilinear, the default of older torchvision releases on tensors     */
 } agym_config;
 
 typedef struct agym_plan agym_plan;   /* opaque: validated config + device coefficient tables */
@@ -195,13 +197,13 @@ AGYM_API int agym_record_step(int32_t n_envs, int is_reset, const double *d_raw_
  * agym_table_aa: ATen antialiased-bilinear weights of one axis (fov_env.py:120,248,278,366-368);
  * h_xmin has n_out entries, h_w has n_out * (*taps) entries (capacity w_capacity floats). */
 AGYM_API int agym_table_cv2(int n_src, int n_dst, int zero_frac_at_border, int32_t *h_s0, int32_t *h_s1, int32_t *h_coef);
-AGYM_API int agym_table_aa(int n_in, int n_out, int32_t *h_xmin, float *h_w, size_t w_capacity, int32_t *taps);
+AGYM_API int agym_table_aa(int n_in, int n_out, int antialias, int32_t *h_xmin, float *h_w, size_t w_capacity, int32_t *taps);
 /* agym_table_blur: the flexible fovea's blur Resize(f) -> Resize(r) along one axis (fov_env.py:276-280) as ONE
  * banded r x r operator: h_xmin [r], h_w [r][*taps] float weights, and the 16-bit fixed-point form the W pass
  * of agym_observe_flexible multiplies with, h_q [r][*halves * 8] (weights * 2^16, every row sums to 2^16).
  * capacity: entries available in h_w and in h_q. */
-AGYM_API int agym_table_blur(int r, int f, int32_t *h_xmin, float *h_w, uint16_t *h_q, size_t capacity, int32_t *taps,
-                             int32_t *halves);
+AGYM_API int agym_table_blur(int r, int f, int antialias, int32_t *h_xmin, float *h_w, uint16_t *h_q, size_t capacity,
+                             int32_t *taps, int32_t *halves);
 
 /* Consumer-side convenience: u8 observations -> the reference's normalised value
  * float32(u) / 255 (atari_env.py:75, dmc_env.py:183) as a pass of its own.  AGYM_DTYPE_F32 is bit-identical to the

@@ -111,8 +111,41 @@ OR_API void or_luma_u8(const uint8_t *src3, size_t npix, int w0, int w1, int w2,
  * ---------------------------------------------------------------------------------- */
 typedef struct { int n_out, maxk; int *xmin, *xsize; double *w; } or_aa_axis_t;
 
+/* antialias=False: what torchvision's Resize did on tensors before antialias=True became its default (SURVEY.md
+ * section 8c, library-version sensitivity) == F.interpolate(bilinear, align_corners=False, antialias=False) == ATen
+ * upsample_bilinear2d: src = scale * (dst + 0.5) - 0.5 clamped at 0, taps {floor(src), +1}, weights {1 - l, l}. */
+static int g_or_antialias = 1;
+OR_API void or_set_antialias(int on) { g_or_antialias = on ? 1 : 0; }
+
+static void or_bilinear_axis_build(or_aa_axis_t *t, int n_in, int n_out, int use_f32)
+{
+    t->n_out = n_out; t->maxk = 2;
+    t->xmin = malloc(sizeof(int) * n_out); t->xsize = malloc(sizeof(int) * n_out);
+    t->w = calloc((size_t)n_out * 2, sizeof(double));
+    for (int i = 0; i < n_out; ++i) {
+        double l1; int i0;
+        if (use_f32) {
+            float scale = (float)n_in / (float)n_out;
+            float src = scale * ((float)i + 0.5f) - 0.5f; if (src < 0.f) src = 0.f;
+            i0 = (int)src; if (i0 > n_in - 1) i0 = n_in - 1;
+            l1 = (double)(src - (float)i0);
+            t->w[2 * i] = (double)(1.0f - (float)l1);
+        } else {
+            double scale = (double)n_in / (double)n_out;
+            double src = scale * (i + 0.5) - 0.5; if (src < 0.0) src = 0.0;
+            i0 = (int)src; if (i0 > n_in - 1) i0 = n_in - 1;
+            l1 = src - i0;
+            t->w[2 * i] = 1.0 - l1;
+        }
+        t->xmin[i] = i0;
+        if (i0 < n_in - 1) { t->xsize[i] = 2; t->w[2 * i + 1] = l1; }
+        else { t->xsize[i] = 1; t->w[2 * i] = 1.0; }
+    }
+}
+
 static void or_aa_axis_build(or_aa_axis_t *t, int n_in, int n_out, int use_f32)
 {
+    if (!g_or_antialias) { or_bilinear_axis_build(t, n_in, n_out, use_f32); return; }
     double scale_d = (double)n_in / (double)n_out;
     float scale_f = (float)n_in / (float)n_out;
     double support_d = scale_d >= 1.0 ? scale_d : 1.0;

@@ -26,7 +26,8 @@ class OraclePath:
 
     def __init__(self, n_envs, frame_stack, obs_size, raw_shape, shards=1, device=None, luma=orc.LUMA_RGB, fov_size=None,
                  fov_init_loc=(0, 0), sensory_action_mode="absolute", sensory_action_space=(0.0, 0.0), peripheral_res=None,
-                 cache_peripheral=True, packed_h2d=True, side_streams=False):
+                 cache_peripheral=True, packed_h2d=True, side_streams=False, antialias=True):
+        self.antialias = bool(antialias)
         self.device = torch.device("cpu")
         self.n_envs, self.frame_stack = int(n_envs), int(frame_stack)
         self.obs_size = tuple(int(v) for v in obs_size)
@@ -150,20 +151,28 @@ class OraclePath:
             return out, (out, self.loc.clone(), self.res.clone() if flexible else None)
         return out
 
+    def _oracle(self, fn, *a, **kw):
+        """The oracle's antialias switch is process wide: set it for this call only."""
+        orc.set_antialias(self.antialias)
+        try:
+            return fn(*a, **kw)
+        finally:
+            orc.set_antialias(True)
+
     def observe_fixed(self, action, variant="crop", ctrl=None, out=None, host_out=False, norm_out=None):
         self._update(action, None, ctrl, False)
-        o = orc.observe_fixed(self._ring, self._head, self.loc.numpy(), self.fov_size, variant)
+        o = self._oracle(orc.observe_fixed, self._ring, self._head, self.loc.numpy(), self.fov_size, variant)
         return self._finish(o, host_out, norm_out=norm_out)
 
     def observe_peripheral(self, action, ctrl=None, out=None, use_cache=True, host_out=False, norm_out=None):
         self._update(action, None, ctrl, False)
-        o = orc.observe_peripheral(self._ring, self._head, self.loc.numpy(), self.fov_size, self.peripheral_res)
+        o = self._oracle(orc.observe_peripheral, self._ring, self._head, self.loc.numpy(), self.fov_size, self.peripheral_res)
         return self._finish(o, host_out, norm_out=norm_out)
 
     def observe_flexible(self, action, action_type=None, variant="mask", ctrl=None, pad=None, out=None, host_out=False, norm_out=None):
         self._update(action, action_type, ctrl, True)
-        o = orc.observe_flexible(self._ring, self._head, self.loc.numpy(), self.res.numpy(), self.fov_size, variant,
-                                 pad=pad if pad is not None else self.obs_size)
+        o = self._oracle(orc.observe_flexible, self._ring, self._head, self.loc.numpy(), self.res.numpy(), self.fov_size, variant,
+                         pad=pad if pad is not None else self.obs_size)
         return self._finish(o, host_out, flexible=True, norm_out=norm_out)
 
     # ---- RecordWrapper counters (restates k_record_step)

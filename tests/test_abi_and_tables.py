@@ -60,11 +60,11 @@ def test_cv2_tables_reproduce_the_fixed_point_resize(shape, out):
     assert np.array_equal(v.astype(np.uint8), orc.cv2_resize_linear(src.astype(np.uint8), out))
 
 
-def _aa_axis(n_in, n_out):
+def _aa_axis(n_in, n_out, antialias=True):
     xmin = np.zeros(n_out, np.int32)
     w = np.zeros(n_out * 128, np.float32)
     taps = C.c_int32()
-    assert _lib.lib().agym_table_aa(n_in, n_out, xmin.ctypes.data, w.ctypes.data, w.size, C.byref(taps)) == 0
+    assert _lib.lib().agym_table_aa(n_in, n_out, int(antialias), xmin.ctypes.data, w.ctypes.data, w.size, C.byref(taps)) == 0
     return xmin, w[:n_out * taps.value].reshape(n_out, taps.value)
 
 
@@ -82,12 +82,12 @@ def test_aa_tables_reproduce_the_antialiased_resize(ish, osh):
     assert np.abs(y - orc.aa_resize(x, osh)).max() <= 1e-4  # float32 weights vs the float64 oracle, u8 LSB
 
 
-def _blur_axis(r, f):
+def _blur_axis(r, f, antialias=True):
     xmin = np.zeros(r, np.int32)
     w = np.zeros(r * 32, np.float32)
     q = np.zeros(r * 32, np.uint16)
     taps, halves = C.c_int32(), C.c_int32()
-    assert _lib.lib().agym_table_blur(r, f, xmin.ctypes.data, w.ctypes.data, q.ctypes.data, w.size,
+    assert _lib.lib().agym_table_blur(r, f, int(antialias), xmin.ctypes.data, w.ctypes.data, q.ctypes.data, w.size,
                                       C.byref(taps), C.byref(halves)) == 0
     return xmin, w[:r * taps.value].reshape(r, taps.value), q[:r * halves.value * 8].reshape(r, halves.value * 8)
 
@@ -125,3 +125,41 @@ def test_standard_vertical_resize_never_samples_every_fifth_raw_row():
     assert len(used) == 168 and not np.any(used % 5 == 2)
     assert set(zip(b0[0::2], b1[0::2])) == {(512, 1536)} and set(zip(b0[1::2], b1[1::2])) == {(1536, 512)}
 
+
+
+@pytest.mark.parametrize("ish,osh", [((84, 84), (20, 20)), ((44, 50), (30, 30)), ((30, 30), (44, 50)), ((84, 84), (84, 20))])
+def test_plain_bilinear_tables_and_oracle_match_torch_without_antialias(ish, osh):
+    """antialias=False (the default of older torchvision releases on tensors): the host tables and
+    the oracle both restate F.interpolate(bilinear, align_corners=False, antialias=False), checked against torch itself."""
+    import torch
+    import torch.nn.functional as F
+    rng = np.random.default_rng(5)
+    x = rng.integers(0, 256, ish).astype(np.float64)
+    want = F.interpolate(torch.from_numpy(x)[None, None], size=osh, mode="bilinear", align_corners=False, antialias=False)[0, 0].numpy()
+    orc.set_antialias(False)
+    try:
+        got_oracle = orc.aa_resize(x, osh)
+    finally:
+        orc.set_antialias(True)
+    assert np.abs(got_oracle - want).max() <= 1e-9
+    xm, ww = _aa_axis(ish[1], osh[1], antialias=False)
+    ym, wh = _aa_axis(ish[0], osh[0], antialias=False)
+    assert ww.shape[1] <= 2 and wh.shape[1] <= 2 and (xm + ww.shape[1] <= ish[1]).all() and (ym + wh.shape[1] <= ish[0]).all()
+    t = np.stack([(x[:, xm[i]:xm[i] + ww.shape[1]] * ww[i]).sum(1) for i in range(osh[1])], 1)
+    y = np.stack([(t[ym[j]:ym[j] + wh.shape[1]] * wh[j][:, None]).sum(0) for j in range(osh[0])], 0)
+    assert np.abs(y - want).max() <= 1e-4
+    assert np.abs(orc.aa_resize(x, osh) - want).max() > 1.0 or ish[1] <= osh[1]   # the antialiased result really differs when downscaling
+
+
+def test_blur_table_without_antialias_composes_the_two_plain_resamples():
+    r, f = 44, 30
+    rng = np.random.default_rng(9)
+    x = rng.integers(0, 256, (3, r)).astype(np.float64)
+    orc.set_antialias(False)
+    try:
+        want = orc.aa_resize(orc.aa_resize(x, (3, f)), (3, r))
+    finally:
+        orc.set_antialias(True)
+    xm, w, q = _blur_axis(r, f, antialias=False)
+    got = np.stack([(x[:, xm[i]:xm[i] + w.shape[1]] * w[i]).sum(1) for i in range(r)], 1)
+    assert np.abs(got - want).max() <= 1e-4

@@ -263,3 +263,47 @@ def test_normalised_second_output_of_the_observe_kernels_is_bit_identical_to_nor
     ref = out.cpu().numpy().astype(np.float32) / np.float32(255.0)
     assert set(np.unique(out.cpu().numpy()).tolist()) == set(range(256))
     assert np.array_equal(no.cpu().numpy().view(np.uint32), ref.view(np.uint32))
+
+
+@pytest.mark.parametrize("kind", ["peripheral_std", "peripheral_other", "peripheral_uncached", "flexible_mask", "flexible_resize_full"])
+def test_plain_bilinear_mode_matches_the_oracle_without_antialias(kind):
+    """antialias=False (older torchvision releases resized tensors without antialiasing): the same
+    kernels on plain-bilinear tables against the oracle's restatement of F.interpolate(..., antialias=False), which a CPU
+    test pins against torch itself.  The results must really differ from the antialiased mode."""
+    rng = np.random.default_rng(31)
+    n, K, fov = 40, 4, (30, 30)
+    periph = (16, 24) if kind == "peripheral_other" else (20, 20)
+    kw = dict(fov_size=fov, sensory_action_mode="absolute", antialias=False)
+    if kind.startswith("peripheral"):
+        kw.update(peripheral_res=periph, cache_peripheral=kind != "peripheral_uncached")
+    p = _path(n, K, **kw)
+    ring, head = _fill(p, rng, n, K, steps=6)
+    loc = np.zeros((n, 2), np.int32)
+    res = np.tile(np.array([fov], np.int32), (n, 1))
+    orc.set_antialias(False)
+    try:
+        for step in range(3):
+            if kind.startswith("peripheral"):
+                a = rng.integers(0, 55, (n, 2)).astype(np.float64)
+                orc.update_loc(a, loc, obs_size=(84, 84), fov_size=fov)
+                got = _np(p.observe_peripheral(a, use_cache=kind != "peripheral_uncached")).astype(np.float64)
+                want = orc.observe_peripheral(ring, head, loc, fov, periph)
+                orc.set_antialias(True)
+                other = orc.observe_peripheral(ring, head, loc, fov, periph)
+                orc.set_antialias(False)
+            else:
+                variant = kind.split("_", 1)[1]
+                atype = rng.integers(0, 2, n).astype(np.int32)
+                a = np.where(atype[:, None] == 1, rng.integers(20, 51, (n, 2)), rng.integers(0, 65, (n, 2))).astype(np.float64)
+                orc.update_loc(a, loc, obs_size=(84, 84), fov_size=fov, atype=atype, res=res)
+                got = _np(p.observe_flexible(a, atype, variant=variant)).astype(np.float64)
+                want = orc.observe_flexible(ring, head, loc, res, fov, variant=variant)
+                orc.set_antialias(True)
+                other = orc.observe_flexible(ring, head, loc, res, fov, variant=variant)
+                orc.set_antialias(False)
+            assert np.array_equal(_np(p.loc), loc)
+            assert np.abs(got - want).max() <= TOL, (kind, step)
+            if step == 2 and kind != "flexible_resize_full":
+                assert np.abs(other - want).max() > 2.0, "the antialiased mode gives visibly different pixels"
+    finally:
+        orc.set_antialias(True)
