@@ -328,42 +328,42 @@ __device__ __forceinline__ void flex_hpass(const FlexGeom &g, const float *s_t1,
     }
 }
 
-// W pass over nrows staged rows: t1[row][sb + x] = 2^-16 * sum_t q[x][t] * X[row][xw[x] + t]; a thread takes
-// column x of rows rp and rp + ceil(nrows / 2) (same weights and shift, two independent IDP.2A chains)
+// W pass over nrows staged rows: t1[row][sb + x] = 2^-16 * sum_t q[x][t] * X[row][xw[x] + t].  A thread OWNS output
+// column x (its weights, first tap and shift stay in registers for the whole env) and walks down the rows of its row
+// group, two rows per iteration (two independent IDP.2A chains): 28 instructions per two outputs instead of the 57 of
+// the item-per-iteration form, whose index arithmetic and weight reloads were a quarter of the kernel (ncu source view).
 template <int NH>
 __device__ __forceinline__ void flex_wpass(const uint32_t *xrow0, int nwxp, const int32_t *s_xw, const uint32_t *s_wq,
                                            float *s_t1, int rwp, int sb, int cb, int rw, int nrows, int tid, const uint32_t *s_magic) {
     const FastDiv fd_rw(rw, s_magic);
-    const int nrp = (nrows + 1) >> 1, dr = fd_rw.div(kFlexThreads), dx = kFlexThreads - dr * rw;
-    int rp = fd_rw.div(tid), x = tid - rp * rw;
-    while (rp < nrp) {
-        const int b = cb + s_xw[x];
-        const uint32_t sh = (uint32_t)(b & 3) * 8u;
-        const uint32_t *sp0 = xrow0 + rp * nwxp + (b >> 2), *sp1 = sp0 + nrp * nwxp;
-        const bool two = rp + nrp < nrows;
-        const uint4 *wq = reinterpret_cast<const uint4 *>(s_wq) + x * NH;
+    const int G = fd_rw.div(kFlexThreads);           // row groups: kFlexThreads / rw >= 3 (rw <= 84)
+    const int g = fd_rw.div(tid), x = tid - g * rw;
+    if (g >= G) return;                              // the kFlexThreads - G * rw threads past the last group
+    const int b = cb + s_xw[x];
+    const uint32_t sh = (uint32_t)(b & 3) * 8u;
+    uint4 q[NH];
+#pragma unroll
+    for (int hh = 0; hh < NH; ++hh) q[hh] = reinterpret_cast<const uint4 *>(s_wq)[x * NH + hh];
+    const uint32_t *sp = xrow0 + g * nwxp + (b >> 2);
+    float *d = s_t1 + g * rwp + sb + x;
+    const int step_s = G * nwxp, step_d = G * rwp;
+    for (int r = g; r < nrows; r += 2 * G, sp += 2 * step_s, d += 2 * step_d) {
+        const bool two = r + G < nrows;
+        const uint32_t *sp1 = two ? sp + step_s : sp;    // the second row of the iteration (the first again past the end)
         uint32_t acc0 = 0u, acc1 = 0u;
 #pragma unroll
         for (int hh = 0; hh < NH; ++hh) {
-            const uint4 q = wq[hh];
-            {
-                const uint32_t a0 = sp0[2 * hh], a1 = sp0[2 * hh + 1], a2 = sp0[2 * hh + 2];
-                const uint32_t lo = __funnelshift_r(a0, a1, sh), hi = __funnelshift_r(a1, a2, sh);
-                acc0 = __dp2a_lo(q.x, lo, acc0); acc0 = __dp2a_hi(q.y, lo, acc0);
-                acc0 = __dp2a_lo(q.z, hi, acc0); acc0 = __dp2a_hi(q.w, hi, acc0);
-            }
-            if (two) {
-                const uint32_t a0 = sp1[2 * hh], a1 = sp1[2 * hh + 1], a2 = sp1[2 * hh + 2];
-                const uint32_t lo = __funnelshift_r(a0, a1, sh), hi = __funnelshift_r(a1, a2, sh);
-                acc1 = __dp2a_lo(q.x, lo, acc1); acc1 = __dp2a_hi(q.y, lo, acc1);
-                acc1 = __dp2a_lo(q.z, hi, acc1); acc1 = __dp2a_hi(q.w, hi, acc1);
-            }
+            const uint32_t a0 = sp[2 * hh], a1 = sp[2 * hh + 1], a2 = sp[2 * hh + 2];
+            const uint32_t c0 = sp1[2 * hh], c1 = sp1[2 * hh + 1], c2 = sp1[2 * hh + 2];
+            const uint32_t lo0 = __funnelshift_r(a0, a1, sh), hi0 = __funnelshift_r(a1, a2, sh);
+            const uint32_t lo1 = __funnelshift_r(c0, c1, sh), hi1 = __funnelshift_r(c1, c2, sh);
+            acc0 = __dp2a_lo(q[hh].x, lo0, acc0); acc0 = __dp2a_hi(q[hh].y, lo0, acc0);
+            acc1 = __dp2a_lo(q[hh].x, lo1, acc1); acc1 = __dp2a_hi(q[hh].y, lo1, acc1);
+            acc0 = __dp2a_lo(q[hh].z, hi0, acc0); acc0 = __dp2a_hi(q[hh].w, hi0, acc0);
+            acc1 = __dp2a_lo(q[hh].z, hi1, acc1); acc1 = __dp2a_hi(q[hh].w, hi1, acc1);
         }
-        float *d = s_t1 + rp * rwp + sb + x;
         d[0] = (float)acc0 * (1.f / 65536.f);
-        if (two) d[nrp * rwp] = (float)acc1 * (1.f / 65536.f);
-        x += dx; rp += dr;
-        if (x >= rw) { x -= rw; ++rp; }
+        if (two) d[step_d] = (float)acc1 * (1.f / 65536.f);
     }
 }
 
@@ -418,18 +418,22 @@ __global__ void __launch_bounds__(kFlexThreads + 32, 2) k_observe_flexible_v3(co
         s_en[e] = q.n;
         if (q.n >= N) return;
         int r = q.r, c = q.c, rh = q.rh, rw = q.rw;
+        double a0 = q.a0, a1 = q.a1;
+        // the control thread's fp64 chain must stay inside its branch: without this fence the compiler speculates the
+        // ~60 fp64 instructions above `if (boss)` and every warp executes them for every env (ncu source view)
+        asm volatile("" : "+d"(a0), "+d"(a1), "+r"(r), "+r"(c));
         if (q.mode == AGYM_FOV_RESET) {
             r = p.init_r; c = p.init_c; rh = p.f_h; rw = p.f_w;
         } else if (q.mode == AGYM_FOV_APPLY) {
             if (q.t == AGYM_ATYPE_FOV_RES) {  // fov_res = action, then re-clamp loc (fov_env.py:322-324)
-                res_from_action(p, q.a0, q.a1, rh, rw);
+                res_from_action(p, a0, a1, rh, rw);
                 r = clip_rint((double)r, 0.0, (double)(p.S_h - rh));
                 c = clip_rint((double)c, 0.0, (double)(p.S_w - rw));
             } else {
-                double v0 = q.a0, v1 = q.a1;
+                double v0 = a0, v1 = a1;
                 if (p.relative) {
-                    v0 = (double)(r + clip_rint(q.a0, p.lo, p.hi));
-                    v1 = (double)(c + clip_rint(q.a1, p.lo, p.hi));
+                    v0 = (double)(r + clip_rint(a0, p.lo, p.hi));
+                    v1 = (double)(c + clip_rint(a1, p.lo, p.hi));
                 }
                 r = clip_rint(v0, 0.0, (double)(p.S_h - rh));
                 c = clip_rint(v1, 0.0, (double)(p.S_w - rw));
