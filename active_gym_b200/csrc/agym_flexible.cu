@@ -332,24 +332,29 @@ __device__ __forceinline__ void flex_hpass(const FlexGeom &g, const float *s_t1,
 // column x (its weights, first tap and shift stay in registers for the whole env) and walks down the rows of its row
 // group, two rows per iteration (two independent IDP.2A chains): 28 instructions per two outputs instead of the 57 of
 // the item-per-iteration form, whose index arithmetic and weight reloads were a quarter of the kernel (ncu source view).
+// The staged rows are the full-width strips of the K frames (strip_w words apart, rows row_w words apart; xrow0 = the
+// first window row of frame k0, c0 = the window's first column): row r of the group is row r % rh of frame r / rh.
 template <int NH>
-__device__ __forceinline__ void flex_wpass(const uint32_t *xrow0, int nwxp, const int32_t *s_xw, const uint32_t *s_wq,
-                                           float *s_t1, int rwp, int sb, int cb, int rw, int nrows, int tid, const uint32_t *s_magic) {
-    const FastDiv fd_rw(rw, s_magic);
+__device__ __forceinline__ void flex_wpass(const uint32_t *xrow0, int rh, int row_w, int strip_w, const int32_t *s_xw, const uint32_t *s_wq,
+                                           float *s_t1, int rwp, int sb, int c0, int rw, int nrows, int tid, const uint32_t *s_magic) {
+    const FastDiv fd_rw(rw, s_magic), fd_rh(rh, s_magic);
+    const int kfix = strip_w - rh * row_w;
     const int G = fd_rw.div(kFlexThreads);           // row groups: kFlexThreads / rw >= 3 (rw <= 84)
     const int g = fd_rw.div(tid), x = tid - g * rw;
     if (g >= G) return;                              // the kFlexThreads - G * rw threads past the last group
-    const int b = cb + s_xw[x];
+    const int b = c0 + s_xw[x];
     const uint32_t sh = (uint32_t)(b & 3) * 8u;
     uint4 q[NH];
 #pragma unroll
     for (int hh = 0; hh < NH; ++hh) q[hh] = reinterpret_cast<const uint4 *>(s_wq)[x * NH + hh];
-    const uint32_t *sp = xrow0 + g * nwxp + (b >> 2);
+    const uint32_t *sp0 = xrow0 + (b >> 2);
     float *d = s_t1 + g * rwp + sb + x;
-    const int step_s = G * nwxp, step_d = G * rwp;
-    for (int r = g; r < nrows; r += 2 * G, sp += 2 * step_s, d += 2 * step_d) {
+    const int step_d = G * rwp;
+    for (int r = g; r < nrows; r += 2 * G, d += 2 * step_d) {
         const bool two = r + G < nrows;
-        const uint32_t *sp1 = two ? sp + step_s : sp;    // the second row of the iteration (the first again past the end)
+        const int r1 = two ? r + G : r;                  // the second row of the iteration (the first again past the end)
+        const uint32_t *sp = sp0 + r * row_w + fd_rh.div(r) * kfix;
+        const uint32_t *sp1 = sp0 + r1 * row_w + fd_rh.div(r1) * kfix;
         uint32_t acc0 = 0u, acc1 = 0u;
 #pragma unroll
         for (int hh = 0; hh < NH; ++hh) {
@@ -383,14 +388,16 @@ __global__ void __launch_bounds__(kFlexThreads + 32, 2) k_observe_flexible_v3(co
     __shared__ int s_en[kWin], s_er[kWin], s_ec[kWin], s_erh[kWin], s_erw[kWin], s_ehd[kWin];
     __shared__ int s_eth[kWin], s_ehw[kWin], s_ehx[kWin], s_enh[kWin], s_eqw[kWin], s_eqx[kWin];
     __shared__ uint32_t s_magic[256];              // FastDiv multipliers of 1..255: a division per divisor and env otherwise
+    __shared__ __align__(8) uint64_t s_bar;        // completion of an env's K strip copies (phase = env count & 1)
     const int tid = threadIdx.x;
     if (tid < 256) s_magic[tid] = tid ? 0xFFFFFFFFu / (uint32_t)tid + 1u : 0u;
+    if (tid == kFlexThreads) { mbar_init(&s_bar, 1); mbar_fence_init(); }
     const bool worker = tid < kFlexThreads;        // warps 0 .. 7/11 compute, the last warp is the control warp
     const bool boss = tid == kFlexThreads;         // its lane 0: env claims, fov updates, TMA stores
-    const int K = p.K, quads = p.S_w >> 2, xcap = quads + 2, plane4 = p.plane >> 2;
+    const int K = p.K, quads = p.S_w >> 2, xcap = quads + 2, strip_w = (p.plane + 16) >> 2;
     const int tile_bytes = K * oh * ow;
     uint32_t *s_tile = reinterpret_cast<uint32_t *>(smem);                          // [K][oh][ow] bytes
-    uint32_t *s_x = s_tile + (tile_bytes >> 2);                                     // [K * rh][nwx + 2] window words
+    uint32_t *s_x = s_tile + (tile_bytes >> 2);                                     // [K][strip_w]: the windows' full-width row strips
     float *s_t1 = reinterpret_cast<float *>(smem + align16((size_t)tile_bytes + 4 * (size_t)K * p.S_h * xcap));  // [kg * rh][rwp]
     uint32_t *s_wq = reinterpret_cast<uint32_t *>(s_t1 + t1_cap);                   // [rw][halves][4]; t1_cap % 4 == 0
     uint64_t *s_wh2 = reinterpret_cast<uint64_t *>(s_wq + p.S_w * 8);               // [rh][th] {w, w}
@@ -448,29 +455,31 @@ __global__ void __launch_bounds__(kFlexThreads + 32, 2) k_observe_flexible_v3(co
             s_enh[e] = ew.taps; s_eqw[e] = ew.w_off; s_eqx[e] = ew.xmin_off;
         }
     };
-    // ---- workers: the K windows of entry e as aligned words, and its W operator, by cp.async (one group)
+    // ---- boss: the K windows of entry e as the full-width strips of their rows, one TMA bulk copy per frame (a strip is
+    // contiguous in the ring; its 16-byte-aligned hull starts `lead` bytes early, the same for every frame because a
+    // plane is a multiple of 16 bytes).  No thread spends instructions on the windows; the strips complete on s_bar.
+    auto fetch_strips = [&](int e) {
+        const int n = s_en[e];
+        if (n >= N) return;
+        const int r0 = s_er[e], rh = s_erh[e], h = s_ehd[e];
+        const uint32_t first = (uint32_t)(r0 * p.S_w), lead = first & 15u;
+        const uint32_t bytes = (lead + (uint32_t)(rh * p.S_w) + 15u) & ~15u;
+        const uint8_t *src = ring + (size_t)n * K * p.plane + (first - lead);
+        mbar_expect_tx(&s_bar, bytes * (uint32_t)K);
+        for (int k = 0; k < K; ++k) {
+            int slot = h + 1 + k;
+            slot -= slot >= K ? K : 0;
+            bulk_g2s(s_x + k * strip_w, src + (size_t)slot * p.plane, bytes, &s_bar);
+        }
+    };
+    // ---- workers: the W operator of entry e by cp.async (one group)
     auto prefetch = [&](int e) {
         const int n = s_en[e];
-        if (n < N) {
-            const int r0 = s_er[e], c0 = s_ec[e], rh = s_erh[e], rw = s_erw[e], h = s_ehd[e];
-            const int wq0 = c0 >> 2, nwx = ((c0 + rw - 1) >> 2) - wq0 + 1, nwxp = nwx + 2;
-            const uint32_t *src = reinterpret_cast<const uint32_t *>(ring) + (size_t)n * K * plane4 + r0 * quads + wq0;
-            const FastDiv fd_w(nwx, s_magic), fd_h(rh, s_magic);
-            const int nrows = K * rh, dr = fd_w.div(kFlexThreads), dw = kFlexThreads - dr * nwx;
-            int row = fd_w.div(tid), w = tid - row * nwx;
-            while (row < nrows) {
-                const int k = fd_h.div(row), y = row - k * rh;
-                int slot = h + 1 + k;
-                slot -= slot >= K ? K : 0;
-                cp_async4(s_x + row * nwxp + w, src + slot * plane4 + y * quads + w);
-                w += dw; row += dr;
-                if (w >= nwx) { w -= nwx; ++row; }
-            }
-            if (rh > p.f_h) {
-                const int32_t *gq = p.pool_i + s_eqw[e], *gx = p.pool_i + s_eqx[e];
-                for (int i = tid; i < rw * s_enh[e]; i += kFlexThreads) cp_async16(s_wq + 4 * i, gq + 4 * i);
-                for (int i = tid; i < rw; i += kFlexThreads) cp_async4(s_xw + i, gx + i);
-            }
+        if (n < N && s_erh[e] > p.f_h) {
+            const int rw = s_erw[e];
+            const int32_t *gq = p.pool_i + s_eqw[e], *gx = p.pool_i + s_eqx[e];
+            for (int i = tid; i < rw * s_enh[e]; i += kFlexThreads) cp_async16(s_wq + 4 * i, gq + 4 * i);
+            for (int i = tid; i < rw; i += kFlexThreads) cp_async4(s_xw + i, gx + i);
         }
         cp_async_commit();
     };
@@ -482,6 +491,7 @@ __global__ void __launch_bounds__(kFlexThreads + 32, 2) k_observe_flexible_v3(co
         finish_env(q0, 0);
         finish_env(q1, 1);
         more = q1.n < N;
+        fetch_strips(0);
     }
     __syncthreads();
     if (worker) prefetch(0);
@@ -503,7 +513,7 @@ __global__ void __launch_bounds__(kFlexThreads + 32, 2) k_observe_flexible_v3(co
         g.rwp = (sb + rw + 3) & ~3;
         g.m_first = word_mask(0, sb, sb + vw);
         g.m_last = word_mask(4 * (g.nq - 1), sb, sb + vw);
-        const int nwxp = ((c0 + rw - 1) >> 2) - (c0 >> 2) + 3;
+        const uint32_t *s_xs = s_x + ((r0 * p.S_w & 15) >> 2);   // first window row of frame 0 (behind the hull's lead)
         int th = 1, nh = 1;
         if (blur) {  // this env's H operator; s_wh2 / s_xh were last read before the previous env's final barrier
             th = s_eth[e];
@@ -515,7 +525,8 @@ __global__ void __launch_bounds__(kFlexThreads + 32, 2) k_observe_flexible_v3(co
             }
         }
         cp_async_commit();
-        cp_async_wait<1>();                    // this thread's part of the windows (and W operator) has landed
+        cp_async_wait<1>();                    // this thread's part of the W operator has landed
+        if (worker) mbar_wait(&s_bar, (uint32_t)j & 1u);   // the strips of this env (the j-th of this CTA) have landed
         if (boss) bulk_wait_read<0>();         // the previous tile has been read by the TMA store
         __syncthreads();                       // #1
         Pend pend;
@@ -536,16 +547,18 @@ __global__ void __launch_bounds__(kFlexThreads + 32, 2) k_observe_flexible_v3(co
             if (k0) __syncthreads();           // the previous group's H pass has read t1
             if (!worker) {
             } else if (blur) {
-                if (nh == 1) flex_wpass<1>(s_x + k0 * rh * nwxp, nwxp, s_xw, s_wq, s_t1, g.rwp, sb, cb, rw, kc * rh, tid, s_magic);
-                else flex_wpass<2>(s_x + k0 * rh * nwxp, nwxp, s_xw, s_wq, s_t1, g.rwp, sb, cb, rw, kc * rh, tid, s_magic);
+                if (nh == 1) flex_wpass<1>(s_xs + k0 * strip_w, rh, quads, strip_w, s_xw, s_wq, s_t1, g.rwp, sb, c0, rw, kc * rh, tid, s_magic);
+                else flex_wpass<2>(s_xs + k0 * strip_w, rh, quads, strip_w, s_xw, s_wq, s_t1, g.rwp, sb, c0, rw, kc * rh, tid, s_magic);
             } else {
                 // the window itself, bit exact: output words (bytes outside the window masked to zero) parked in t1
-                const FastDiv fd_nq(g.nq, s_magic);
+                const FastDiv fd_nq(g.nq, s_magic), fd_rh(rh, s_magic);
                 const uint32_t sh = (uint32_t)(cb - sb) * 8u;
                 uint32_t *t1w = reinterpret_cast<uint32_t *>(s_t1);
+                const uint32_t *sp0 = s_xs + k0 * strip_w + (c0 >> 2);
                 for (int i = tid; i < kc * rh * g.nq; i += kFlexThreads) {
                     const int row = fd_nq.div(i), q = i - row * g.nq;
-                    const uint32_t *sp = s_x + (k0 * rh + row) * nwxp + q;
+                    const int kk = fd_rh.div(row), y = row - kk * rh;
+                    const uint32_t *sp = sp0 + kk * strip_w + y * quads + q;
                     uint32_t word = __funnelshift_r(sp[0], sp[1], sh);
                     if (q == 0) word &= g.m_first;
                     if (q == g.nq - 1) word &= g.m_last;
@@ -554,7 +567,10 @@ __global__ void __launch_bounds__(kFlexThreads + 32, 2) k_observe_flexible_v3(co
             }
             if (last) cp_async_wait<0>();      // H operator
             __syncthreads();                   // #2: t1 complete; after the last group s_x / s_wq / s_xw are free
-            if (last && boss) finish_env(pend, (j + 2) & (kWin - 1));  // read by the prefetch after the NEXT env's #2
+            if (last && boss) {
+                fetch_strips((j + 1) & (kWin - 1));                    // s_x is free: the next env's windows
+                finish_env(pend, (j + 2) & (kWin - 1));                // read by the prefetch after the NEXT env's #2
+            }
             if (!worker) continue;
             if (last) prefetch((j + 1) & (kWin - 1));
             if (blur) {
@@ -623,6 +639,7 @@ cudaError_t launch_observe_flexible(const DevPlan &p, const uint8_t *ring, const
         const size_t room = budget > fixed ? ((budget - fixed) / 4) & ~size_t(3) : 0;
         const size_t t1_cap = std::min(all, room);
         if (tile % 16 == 0 && ow % 4 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 && t1_cap >= one &&
+            p.plane % 16 == 0 && p.S_w % 4 == 0 && (reinterpret_cast<uintptr_t>(ring) & 15) == 0 &&   // strip copies
             (size_t)p.K * p.f_h * (p.S_w / 4 + 1) <= t1_cap) {
             const size_t fs = fixed + 4 * t1_cap;
             int dev = 0, sms = 148;
