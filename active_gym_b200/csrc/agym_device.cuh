@@ -49,6 +49,8 @@ struct FastDiv {
     __device__ __forceinline__ explicit FastDiv(int32_t dd) : magic(0xFFFFFFFFu / (uint32_t)dd + 1u), d(dd) {}
     // multiplier from a table of 0xFFFFFFFF / d + 1 (d < 256) instead of an integer division
     __device__ __forceinline__ FastDiv(int32_t dd, const uint32_t *table) : magic(table[dd]), d(dd) {}
+    // multiplier computed on the host (0xFFFFFFFF / d + 1)
+    __device__ __forceinline__ FastDiv(int32_t dd, uint32_t m) : magic(m), d(dd) {}
     // exact for n * d < 2^32 (all indices here are < 2^24, divisors < 2^8)
     __device__ __forceinline__ int32_t div(int32_t n) const { return d == 1 ? n : (int32_t)__umulhi((uint32_t)n, magic); }
 };
@@ -418,6 +420,7 @@ const bool g_disable_tma = getenv("AGYM_NO_TMA") != nullptr;
 const bool g_flex_old = getenv("AGYM_FLEX_OLD") != nullptr;
 // AGYM_CROP_OLD=1 forces the byte-gather crop kernel (A/B comparisons)
 const bool g_crop_old = getenv("AGYM_CROP_OLD") != nullptr;
+const bool g_crop_v2 = getenv("AGYM_CROP_V2") != nullptr;   // timing experiments: the round-2 crop kernel instead of v3
 // AGYM_STD_NOFS=1: the standard-geometry peripheral kernel stages the fovea with per-thread 4-byte copies (A/B comparisons)
 const bool g_std_nofs = getenv("AGYM_STD_NOFS") != nullptr;
 // AGYM_INGEST_UNITS=n: units (shared-memory stages) per env of the TMA ingest kernel (tuning)
