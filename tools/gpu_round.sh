@@ -14,7 +14,7 @@ echo "ncu launches rc=$?"
 $CMD > $O/plain_$TAG.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:'k_ingest_gray_std|k_ingest_atari_tma|k_observe_peripheral' -s 8 -c 4 -f -o $O/prof_$TAG $CMD > $O/ncu_f_$TAG.log 2>&1
 echo "ncu full rc=$?"
-for pair in "atari_fixed:k_ingest_atari_tma:rgb" "atari_flexible:k_observe_flexible_v3:flex" "dmc_fixed:k_ingest_dmc|k_observe_fixed_crop_v2:dmc"; do
+for pair in "atari_fixed:k_ingest_atari_tma:rgb" "atari_flexible:k_observe_flexible_v3:flex" "dmc_fixed:k_ingest_dmc|k_observe_fixed_crop:dmc"; do
   w=${pair%%:*}; rest=${pair#*:}; k=${rest%%:*}; t=${rest#*:}
   C2="python bench.py --workload $w --steps 3 --warmup 3 --no-cpu-baseline --no-e2e --only"
   $C2 > $O/plain_${TAG}_$t.log 2>&1 &&
