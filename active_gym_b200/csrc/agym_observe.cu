@@ -224,7 +224,8 @@ __global__ void __launch_bounds__(kCropWarps * 32) k_observe_fixed_crop_v2(const
 // load, four byte loads and three PRMTs — and parks them in a shared-memory tile that holds the CTA's envs back to back,
 // (iii) the tile leaves as ONE TMA bulk store per CTA (8 envs are a multiple of 16 bytes whatever the window), or as
 // coalesced words from the last, partial CTA.  F_W != 0 fixes the window width at compile time (every loop unrolls, no
-// per-word bookkeeping: ~380 instead of ~1,500 warp-instructions per env); F_W == 0 is the same code for any width.
+// per-word bookkeeping); F_W == 0 is the same code for any width.  Measured: the crop is bound by its
+// scattered 64-byte DRAM granules, not by instructions — v3 is 4-9 % faster than v2 away from 8,192 envs, equal there.
 struct CropV3Args {
     int nch;                // 16-byte chunks per staged row: (f_w + 30) / 16
     int g, gw, ngroups;     // rows / output words per group, groups per env

@@ -20,7 +20,7 @@ HOT = {
     "k_observe_peripheral_std_4_fs": r"k_observe_peripheral_stdILi4ELi0ELb1E",
     "k_ingest_atari_tma_rgb": r"k_ingest_atari_tmaILi480ELi84ELi3ELb1ELi2E",
     "k_observe_flexible_v3_mask": r"k_observe_flexible_v3ILi1E",
-    "k_observe_fixed_crop": r"k_observe_fixed_crop_v\d",
+    "k_observe_fixed_crop_v3_30": r"k_observe_fixed_crop_v3ILi30E",
     "k_ingest_dmc": r"k_ingest_dmc",
 }
 MNEM = ("UTMALDG", "UTMASTG", "UBLKCP", "SYNCS", "LDGSTS", "IDP", "FFMA2", "FADD2", "IMAD.HI", "PRMT", "ATOMG", "BAR.SYNC",
