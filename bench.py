@@ -134,12 +134,20 @@ def _code_only(text):
     return "\n".join(out)
 
 
-def sources_hash():
+# the translation units a workload's two kernels are compiled from (the shared headers, the launcher / plan code and
+# the coefficient tables count for every workload)
+_KERNEL_TUS = {"atari_peripheral": ("agym_ingest_std.cu", "agym_observe.cu"), "atari_fixed": ("agym_ingest.cu", "agym_observe.cu"),
+               "atari_flexible": ("agym_ingest_std.cu", "agym_flexible.cu"), "dmc_fixed": ("agym_ingest.cu", "agym_observe.cu")}
+
+
+def sources_hash(workload=None):
     """Hash of the kernel sources' CODE (comments and blank lines do not count): ties profiles/traffic.json (ncu DRAM
-    bytes) to the code it was captured on."""
+    bytes) to the code it was captured on.  With `workload`, only the files that workload's kernels are built from."""
     h = hashlib.sha256()
     d = os.path.join(ROOT, "active_gym_b200", "csrc")
     for f in sorted(os.listdir(d)):
+        if workload is not None and f.endswith(".cu") and f != "agym_abi.cu" and f not in _KERNEL_TUS[workload]:
+            continue
         if f.endswith((".cu", ".cuh", ".cpp", ".h")):
             with open(os.path.join(d, f), "r", encoding="utf-8", errors="replace") as fh:
                 h.update(f.encode() + b"\0" + _code_only(fh.read()).encode())
@@ -745,14 +753,16 @@ def measure_device(torch, dist, device, world, wname, n, steps, warmup, peak, pe
                        "alg_bytes_per_obs": nb,
                        "achieved_gbs": nb * wl.n / avg / 1e9, "obs_per_s": wl.n / avg}
     dom = max(kern, key=lambda k: kern[k]["ms"])
-    tr = traffic_db.get("workloads", {}).get(wname, {}).get(dom) if traffic_db.get("sources_sha16") == sources_hash() else None
+    captured_on = traffic_db.get("sources_sha16", {})
+    captured_on = captured_on.get(wname) if isinstance(captured_on, dict) else None
+    tr = traffic_db.get("workloads", {}).get(wname, {}).get(dom) if captured_on == sources_hash(wname) else None
     out["kernels"] = kern
     out["alg_bytes_per_obs"] = bytes_
     out["roofline"] = {
         "bound": "hbm", "kernel": f"{dom}: {kern[dom]['kernel']}", "achieved": kern[dom]["achieved_gbs"], "peak": peak,
         "unit": "GB/s", "frac": kern[dom]["achieved_gbs"] / peak, "traffic": tr,
         "traffic_source": ("profiles/traffic.json: ncu dram__bytes_read.sum + dram__bytes_write.sum per launch, captured on sources "
-                           + str(traffic_db.get("sources_sha16"))) if tr is not None else
+                           + str(captured_on)) if tr is not None else
                           "null: profiles/traffic.json was captured on other kernel sources than the ones running (or has no entry)",
         "peak_source": peak_src, "peak_nominal": 8000.0, "frac_nominal": kern[dom]["achieved_gbs"] / 8000.0,
         "alg_bytes_per_launch": kern[dom]["alg_bytes_per_obs"] * wl.n,

@@ -61,13 +61,16 @@ def main():
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     sys.path.insert(0, ROOT)
     from bench import sources_hash  # the same hash bench.py compares against: traffic is only reported for matching sources
-    sha = sources_hash()
+    sha = sources_hash(workload)   # of the files this workload's kernels are built from
     try:
         tj = json.load(open(tpath))
     except Exception:
         tj = {}
-    if tj.get("sources_sha16") != sha:  # captured on other kernel sources: start over
-        tj = {"sources_sha16": sha, "workloads": {}, "source": {}}
+    if not isinstance(tj.get("sources_sha16"), dict):
+        tj = {"sources_sha16": {}, "workloads": {}, "source": {}}
+    if tj["sources_sha16"].get(workload) != sha:  # captured on other kernel sources: this workload starts over
+        tj["workloads"][workload] = {}
+    tj["sources_sha16"][workload] = sha
     tj["workloads"].setdefault(workload, {})
     for kind, v in traffic.items():
         tj["workloads"][workload][kind] = sum(v) / len(v)
