@@ -11,9 +11,11 @@ Workloads (BASELINE.json configs[1..4]; per-GPU env counts, weak scaling):
   atari_peripheral  configs[3]  N=16384  gray 210x160, fovea 30 + periphery 20, relative   (default:
                     the configuration the north-star target "foveal+peripheral 84x84x4 obs/s" is quoted on)
   atari_fixed       configs[1]  N=4096   RGB 210x160x3, fovea 30 crop, relative
+  atari_fixed_gray  configs[1]  N=4096   the same with gray 210x160 input (SURVEY 8d's gray-input variant: the reference's
+                    boundary is ALE's gray screen, which is what the CPU arm is fed)
   atari_flexible    configs[2]  N=4096   gray, per-env res 20..50, mask_out output
   dmc_fixed         configs[4]  N=8192   RGB 84x84x3, fovea 30 crop, K=3
-The line's `value` / `roofline` / `e2e` / `cpu_baseline` are those of --workload; the other three configs are timed
+The line's `value` / `roofline` / `e2e` / `cpu_baseline` are those of --workload; the other configs are timed
 briefly in the same run and reported under `workloads`, and configs[3] as literally stated in BASELINE.json (a GLOBAL
 batch of 16,384 envs sharded by env index over the GPUs, step captured in a CUDA graph) under `strong_scaling`.
 
@@ -69,6 +71,10 @@ WORKLOADS = {
                              K=4, raw=(210, 160, 1), fov=(30, 30), periph=(20, 20), mode="relative", variant="crop"),
     "atari_fixed": dict(config="configs[1] AtariFixedFovealEnv", kind="atari", wrapper="fixed", n=4096, K=4,
                         raw=(210, 160, 3), fov=(30, 30), periph=None, mode="relative", variant="crop"),
+    # SURVEY 8d's gray-input variant of configs[1] (81,456 B/obs): the reference's real boundary is ALE's GRAY screen, which is
+    # also what the CPU arm is fed; the RGB form above pays the luma and 3x the PCIe bytes on the GPU side only
+    "atari_fixed_gray": dict(config="configs[1] AtariFixedFovealEnv, gray-input variant", kind="atari", wrapper="fixed", n=4096, K=4,
+                             raw=(210, 160, 1), fov=(30, 30), periph=None, mode="relative", variant="crop"),
     "atari_flexible": dict(config="configs[2] AtariFlexibleFovealEnv", kind="atari", wrapper="flexible", n=4096, K=4,
                            raw=(210, 160, 1), fov=(30, 30), periph=None, mode="absolute", variant="mask"),
     "dmc_fixed": dict(config="configs[4] DMCFixedFovealEnv", kind="dmc", wrapper="fixed", n=8192, K=3,
@@ -78,6 +84,7 @@ S = (84, 84)
 KERNEL_NAMES = {  # the kernels the two legs of a step launch for the benchmark geometries (GPUTEST / ncu launch lists)
     ("atari_peripheral", "ingest"): "k_ingest_gray_std<160,true,2>", ("atari_peripheral", "observe"): "k_observe_peripheral_std<4,0,true>",
     ("atari_fixed", "ingest"): "k_ingest_atari_tma<480,84,3,true,2>", ("atari_fixed", "observe"): "k_observe_fixed_crop_v3<30>",
+    ("atari_fixed_gray", "ingest"): "k_ingest_gray_std<160,false,2>", ("atari_fixed_gray", "observe"): "k_observe_fixed_crop_v3<30>",
     ("atari_flexible", "ingest"): "k_ingest_gray_std<160,false,2>", ("atari_flexible", "observe"): "k_observe_flexible_v3<MASK>",
     ("dmc_fixed", "ingest"): "k_ingest_dmc", ("dmc_fixed", "observe"): "k_observe_fixed_crop_v3<30>",
 }
@@ -137,6 +144,7 @@ def _code_only(text):
 # the translation units a workload's two kernels are compiled from (the shared headers, the launcher / plan code and
 # the coefficient tables count for every workload)
 _KERNEL_TUS = {"atari_peripheral": ("agym_ingest_std.cu", "agym_observe.cu"), "atari_fixed": ("agym_ingest.cu", "agym_observe.cu"),
+               "atari_fixed_gray": ("agym_ingest_std.cu", "agym_observe.cu"),
                "atari_flexible": ("agym_ingest_std.cu", "agym_flexible.cu"), "dmc_fixed": ("agym_ingest.cu", "agym_observe.cu")}
 
 
