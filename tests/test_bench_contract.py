@@ -48,3 +48,26 @@ def test_b200_arm_fails_loudly_without_a_gpu():
     r = _run("--steps", "1", "--warmup", "1", "--no-cpu-baseline", "--no-e2e")
     assert r.returncode != 0
     assert "CUDA" in (r.stderr + r.stdout) or "cuda" in (r.stderr + r.stdout)
+
+
+def test_traffic_capture_is_tied_to_the_code_it_was_measured_on():
+    """roofline.traffic comes from profiles/traffic.json only while the code of the workload's kernels is what the ncu
+    capture ran: the hash ignores comments and blank lines, covers the workload's own translation units plus the shared
+    headers / launcher, and the committed captures match the committed sources."""
+    sys.path.insert(0, ROOT)
+    import bench
+    a = "int x = 1; // note\n\n  /* block\n comment */ const char *s = \"a//b\";  // tail\n"
+    assert bench._code_only(a) == 'int x = 1;\nconst char *s = "a//b";'
+    assert bench._code_only(a) == bench._code_only("int x = 1;\n  const char *s = \"a//b\";")
+    assert bench._code_only("int x = 2;") != bench._code_only("int x = 1;")
+    # a workload's hash covers only the translation units its kernels come from
+    assert bench.sources_hash("atari_fixed") == bench.sources_hash("dmc_fixed")           # same two TUs
+    assert bench.sources_hash("atari_flexible") != bench.sources_hash("atari_peripheral")
+    assert set(bench._KERNEL_TUS) == set(bench.WORKLOADS)
+    with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+        tj = json.load(f)
+    import warnings
+    for w, sha in tj["sources_sha16"].items():
+        assert w in bench.WORKLOADS and tj["workloads"][w], w
+        if sha != bench.sources_hash(w):   # legitimate (bench.py then prints traffic = null), but worth a line in the test log
+            warnings.warn(f"profiles/traffic.json: the capture of {w} is stale (re-run tools/ncu_summary.py on a fresh ncu report)")
