@@ -43,7 +43,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
     objdir = os.path.join(HERE, "lib", "obj")
     os.makedirs(objdir, exist_ok=True)
-    compile_flags = [f for f in NVCC_FLAGS if f != "-shared"] + (["-Xptxas", "-v"] if verbose else [])
+    # AGYM_NVCC_EXTRA: extra compiler flags (-D tuning switches) for timing experiments
+    compile_flags = [f for f in NVCC_FLAGS if f != "-shared"] + (["-Xptxas", "-v"] if verbose else []) + os.environ.get("AGYM_NVCC_EXTRA", "").split()
 
     def compile_one(src: str):
         obj = os.path.join(objdir, os.path.splitext(src)[0] + ".o")
