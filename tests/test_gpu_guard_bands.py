@@ -147,3 +147,59 @@ def test_flexible_step_stays_inside_its_buffers(n, variant):
     assert np.array_equal(g["loc"].t.cpu().numpy(), loc) and np.array_equal(g["res"].t.cpu().numpy(), res)
     want = orc.observe_flexible(ring, head, loc, res, fov, variant=variant)
     assert np.abs(out.t.cpu().numpy().astype(np.float64) - want).max() <= 0.5 + 1e-2
+
+
+@pytest.mark.parametrize("kind", ["peripheral", "flexible", "fixed_rgb", "dmc"])
+def test_a_step_is_deterministic_whatever_the_scheduling(kind):
+    """Racecheck substitute: the same step from the same state, six times, must give bit-identical state and outputs —
+    the persistent kernels hand envs to CTAs dynamically (atomic claims, whichever CTA is free), so a shared-memory or
+    pipeline race shows up as a run-to-run difference."""
+    rng = np.random.default_rng(11)
+    n, fov = 2500, (30, 30)
+    K = 3 if kind == "dmc" else 4
+    raw = {"peripheral": (210, 160, 1), "flexible": (210, 160, 1), "fixed_rgb": (210, 160, 3), "dmc": (84, 84, 3)}[kind]
+    p, g = _path(n, K, raw, fov, (20, 20) if kind == "peripheral" else None, mode="relative" if kind != "flexible" else "absolute")
+
+    def frames():
+        if kind == "dmc":
+            return (rng.integers(0, 256, (n,) + raw, dtype=np.uint8),)
+        return tuple(rng.integers(0, 256, (2, n) + (raw if raw[2] == 3 else raw[:2]), dtype=np.uint8))
+
+    def ingest(fr, fl):
+        p.ingest_dmc(fr[0], fl) if kind == "dmc" else p.ingest_atari(fr[0], fr[1], fl)
+
+    def observe(a, at, ctrl=None):
+        if kind == "peripheral":
+            return p.observe_peripheral(a, ctrl=ctrl)
+        if kind == "flexible":
+            return p.observe_flexible(a, at, variant="mask", ctrl=ctrl)
+        return p.observe_fixed(a, ctrl=ctrl)
+
+    first = np.full(n, 5, np.uint8)
+    ingest(frames(), first)
+    observe(None, None, ctrl="reset")
+    for _ in range(K):
+        ingest(frames(), np.full(n, 1 if kind == "dmc" else 3, np.uint8))
+    torch.cuda.synchronize()
+    state0 = {k: v.t.clone() for k, v in g.items()}
+    fr = frames()
+    fl = _flags(n, 1, rng)
+    if kind == "dmc":
+        fl = np.where(fl == 8, 8, np.where(fl & 4, 5, 1)).astype(np.uint8)
+    at = rng.integers(0, 2, n).astype(np.int32)
+    a = rng.integers(-10, 11, (n, 2)).astype(np.float64)
+    if kind == "flexible":
+        a = np.where(at[:, None] == 1, rng.integers(20, 51, (n, 2)), rng.integers(0, 55, (n, 2))).astype(np.float64)
+    ref = None
+    for rep in range(6):
+        for k, v in g.items():
+            v.t.copy_(state0[k])
+        ingest(fr, fl)
+        out = observe(a, at)
+        torch.cuda.synchronize()
+        snap = [out.clone()] + [v.t.clone() for v in g.values()]
+        if ref is None:
+            ref = snap
+        else:
+            assert all(torch.equal(x, y) for x, y in zip(ref, snap)), rep
+    assert all(v.intact() for v in g.values())
